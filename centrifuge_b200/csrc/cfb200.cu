@@ -1,0 +1,917 @@
+// cfb200.cu -- kernels + C ABI (include/cfb200.h) of the B200-native classification path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo (see centrifuge_b200/build.py).
+#include "../../include/cfb200.h"
+#include "cf_index.h"
+#include "cf_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <string>
+#include <vector>
+
+using namespace cfb;
+
+// =======================================================================================
+// k_search
+// =======================================================================================
+enum { M_DONE = 0, M_FTAB = 1, M_LF = 2 };
+
+struct Walk {            // group-uniform state of one greedy strand walk
+	const uint8_t* fw; uint32_t rlen; int strand; uint32_t tid;
+	uint32_t cur, dep, offset, nh;
+	uint64_t top, bot, fi;
+	uint32_t tnext, tend;
+	int mode;
+};
+
+struct SearchArgs {
+	IndexView v; Params p; BatchView b;
+	HitRec* hits; uint32_t* nhits; uint32_t cap;
+	unsigned int* task_ctr; uint32_t ntasks, chunk;
+	unsigned int* overflow;
+	Counters* ctr;
+};
+
+template <bool COUNT>
+struct SearchCtx {
+	const SearchArgs& a; unsigned gmask, gbase, gl;
+	unsigned long long c_ps, c_ft, c_sides, c_lf;
+	__device__ __forceinline__ SearchCtx(const SearchArgs& a_) : a(a_), c_ps(0), c_ft(0), c_sides(0), c_lf(0) {
+		const unsigned lane = threadIdx.x & 31;
+		gl = lane & 7; gbase = lane & 24; gmask = 0xFFu << gbase;
+	}
+	__device__ __forceinline__ void emit(Walk& w, uint64_t top, uint64_t bot, uint32_t off, uint32_t len) {
+		if(w.nh < a.cap) {
+			if(gl == 0) { HitRec* h = a.hits + (size_t)w.tid * a.cap + w.nh; h->top = top; h->bot = bot; h->bwoff = off; h->len = len; }
+		} else if(gl == 0) atomicExch(a.overflow, 1u);
+		w.nh++;
+	}
+	// pick the next task of this group (or M_DONE); sets fw/rlen/strand/tid and cur = 0
+	__device__ __forceinline__ bool next_task(Walk& w) {
+		for(;;) {
+			if(w.tnext >= w.tend) {
+				unsigned base = 0;
+				if(gl == 0) base = atomicAdd(a.task_ctr, a.chunk);
+				base = __shfl_sync(gmask, base, gbase);
+				if(base >= a.ntasks) { w.mode = M_DONE; return false; }
+				w.tnext = base; w.tend = min(base + a.chunk, a.ntasks);
+			}
+			w.tid = w.tnext++;
+			const uint32_t per = 2u * (uint32_t)a.b.n_mates;
+			const uint32_t unit = w.tid / per, rem = w.tid - unit * per;
+			const int mate = (int)(rem >> 1);
+			w.strand = (int)(rem & 1);
+			const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
+			w.nh = 0;
+			w.rlen = a.b.len[mate][unit];
+			if(!((fl >> mate) & 1) || w.rlen == 0) { if(gl == 0) a.nhits[w.tid] = 0; continue; }
+			w.fw = a.b.bases + a.b.off[mate][unit];
+			w.cur = 0;
+			return true;
+		}
+	}
+	__device__ __forceinline__ void finish_task(Walk& w) { if(gl == 0) a.nhits[w.tid] = w.nh; }
+
+	// Starts partial searches at w.cur until one needs the ftab (mode M_FTAB) or work runs out.
+	__device__ __forceinline__ void start_search(Walk& w) {
+		const uint32_t fc = (uint32_t)a.v.ftab_chars;
+		for(;;) {
+			if(COUNT) c_ps++;
+			w.offset = w.cur;
+			const uint32_t left = w.rlen - w.cur;
+			if(left < fc) {                               // hi_aligner.h:939-949
+				emit(w, kOff, kOff, w.offset, w.rlen - w.offset);
+				finish_task(w);
+				if(!next_task(w)) return;
+				continue;
+			}
+			uint64_t fi = 0; int bad = -1;
+			for(uint32_t i = 0; i < fc; i++) {            // chars rlen-cur-1-i, i.e. right to left
+				const int c = seq_at(w.fw, w.rlen, w.strand, w.rlen - w.cur - 1 - i);
+				if(c > 3) { bad = (int)i; break; }
+				fi |= (uint64_t)c << (2 * i);             // leftmost base ends up most significant
+			}
+			if(bad >= 0) {                                // hi_aligner.h:951-966
+				const uint32_t hl = (uint32_t)bad + 1;
+				w.cur += hl;
+				emit(w, kOff, kOff, w.offset, hl);
+				if(after_hit(w, hl)) continue; else return;
+			}
+			w.fi = fi; w.mode = M_FTAB;
+			return;
+		}
+	}
+	// searchForwardAndReverse restart policy (classifier.h:686-766).  Returns true if another
+	// partial search must start at w.cur on the same or a new task, false if the group is done.
+	__device__ __forceinline__ bool after_hit(Walk& w, uint32_t hlen) {
+		bool done = w.cur >= w.rlen;
+		if(!done) {
+			if(hlen > a.p.increment) w.cur += 1;
+			if(w.cur + a.p.min_hitlen >= w.rlen) done = true;
+		}
+		if(done) { finish_task(w); if(!next_task(w)) return false; }
+		return true;
+	}
+	__device__ __forceinline__ void hit_and_restart(Walk& w) {
+		const uint32_t hl = w.dep - w.offset;
+		emit(w, w.top, w.bot, w.offset, hl);
+		w.cur = w.dep;
+		if(after_hit(w, hl)) start_search(w);
+	}
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kSearchThreads) k_search(const SearchArgs a) {
+	SearchCtx<COUNT> cx(a);
+	const unsigned gl = cx.gl, gmask = cx.gmask, gbase = cx.gbase;
+	const uint4* sides4 = reinterpret_cast<const uint4*>(a.v.sides);
+	const uint4* ftab4 = reinterpret_cast<const uint4*>(a.v.ftab);
+	Walk w; w.tnext = w.tend = 0; w.mode = M_DONE; w.nh = 0; w.tid = 0; w.rlen = 0; w.cur = 0; w.dep = 0; w.offset = 0; w.top = w.bot = w.fi = 0; w.strand = 0; w.fw = nullptr;
+	if(cx.next_task(w)) cx.start_search(w);
+
+	while(__any_sync(0xffffffffu, w.mode != M_DONE)) {
+		// ---------------- single fetch point ----------------
+		const uint4* pa = nullptr; const uint4* pb = nullptr;
+		uint32_t offT = 0, offB = 0; uint64_t sT = 0, sB = 0; bool range = false, same = true;
+		int c = 0;
+		if(w.mode == M_FTAB) {
+			if(gl < 2) pa = ftab4 + ((w.fi + gl) >> 1);
+		} else if(w.mode == M_LF) {
+			sT = w.top / 384; offT = (uint32_t)(w.top - sT * 384);
+			pa = sides4 + sT * 8 + gl;
+			const uint64_t spread = w.bot - w.top;
+			range = spread != 1;
+			sB = sT; offB = offT;
+			if(range) {
+				same = spread < (uint64_t)(384 - offT);   // initFromTopBot bt2_idx.h:326-349
+				if(same) offB = offT + (uint32_t)spread;
+				else { sB = w.bot / 384; offB = (uint32_t)(w.bot - sB * 384); pb = sides4 + sB * 8 + gl; }
+			}
+			c = seq_at(w.fw, w.rlen, w.strand, w.rlen - w.dep - 1);
+		}
+		uint4 da = make_uint4(0, 0, 0, 0), db = make_uint4(0, 0, 0, 0);
+		if(pa) da = __ldg(pa);
+		if(pb) db = __ldg(pb);
+		// ---------------- consume ----------------
+		if(w.mode == M_FTAB) {
+			const uint64_t lo = (uint64_t)da.x | ((uint64_t)da.y << 32), hi = (uint64_t)da.z | ((uint64_t)da.w << 32);
+			const uint64_t mine = ((w.fi + gl) & 1) ? hi : lo;
+			const uint64_t e0 = __shfl_sync(gmask, mine, gbase), e1 = __shfl_sync(gmask, mine, gbase + 1);
+			if(COUNT) cx.c_ft++;
+			w.top = ftab_hi(a.v, e0); w.bot = ftab_lo(a.v, e1);
+			w.dep = w.cur + (uint32_t)a.v.ftab_chars;
+			if(w.bot <= w.top) {                          // hi_aligner.h:971-982
+				const uint32_t hl = w.dep - w.offset;
+				cx.emit(w, kOff, kOff, w.offset, hl);
+				w.cur = w.dep;
+				if(cx.after_hit(w, hl)) cx.start_search(w);
+			} else if(w.dep < w.rlen) w.mode = M_LF;
+			else cx.hit_and_restart(w);
+		} else if(w.mode == M_LF) {
+			bool fail = c > 3;
+			uint64_t t = 0, b = 0;
+			if(!fail) {
+				const uint32_t rep = (uint32_t)c * 0x55555555u;
+				const uint4& dsel = same ? da : db;
+				int nT = (int)offT - 64 * (int)gl; int nB = (int)offB - 64 * (int)gl;
+				uint32_t cT = 0, cB = 0;
+				if(gl < 6) { cT = lane_count(da, rep, nT < 0 ? 0 : (nT > 64 ? 64 : nT)); cB = lane_count(dsel, rep, nB < 0 ? 0 : (nB > 64 ? 64 : nB)); }
+				const uint32_t packed = group_sum(cT | (cB << 16), gmask);
+				const uint64_t occT = group_occ(da, c, gmask, gbase);
+				const uint64_t occB = group_occ(dsel, c, gmask, gbase);
+				const int rowc = group_char(da, offT, gmask, gbase);
+				uint64_t rT = packed & 0xFFFFu, rB = packed >> 16;
+				if(c == 0) {
+					if(sT == a.v.zside && a.v.zoffc < offT) rT--;
+					if(sB == a.v.zside && a.v.zoffc < offB) rB--;
+				}
+				t = a.v.fchr[c] + occT + rT;
+				if(range) {
+					b = a.v.fchr[c] + occB + rB;
+					if(COUNT) { cx.c_lf += 2; cx.c_sides += same ? 1 : 2; }
+				} else {                                  // mapLF1 bt2_idx.h:2910-2933
+					if(COUNT) { cx.c_lf += 1; cx.c_sides += 1; }
+					if(rowc != c || w.top == a.v.zoff) fail = true;
+					b = t + 1;
+				}
+				if(b <= t) fail = true;
+			}
+			if(fail) cx.hit_and_restart(w);
+			else {
+				w.top = t; w.bot = b; w.dep++;
+				if(w.dep >= w.rlen) cx.hit_and_restart(w);
+			}
+		}
+	}
+	if(COUNT && gl == 0 && a.ctr) {
+		atomicAdd(&a.ctr->partial_searches, cx.c_ps); atomicAdd(&a.ctr->ftab_probes, cx.c_ft);
+		atomicAdd(&a.ctr->sides_search, cx.c_sides); atomicAdd(&a.ctr->lf_steps, cx.c_lf);
+	}
+}
+
+// =======================================================================================
+// k_prep / k_rows / k_score (thread per unit)
+// =======================================================================================
+struct UnitArgs {
+	IndexView v; Params p; BatchView b;
+	HitRec* hits; uint32_t* nhits; uint32_t cap;
+	uint32_t* nrows;            // per unit
+	const uint64_t* row_off;    // exclusive scan of nrows (n_units+1)
+	uint64_t* rows; uint32_t* ids; uint64_t rows_cap;
+	Entry* entries; TaxCnt* tcs; OutRec* recs_sparse; uint32_t* nout;
+	unsigned int* overflow;
+	Counters* ctr;
+};
+
+__device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, UnitHits& u, const uint8_t* fw[2]) {
+	const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
+	u.n_mates = 0;
+	for(int m = 0; m < a.b.n_mates; m++) {
+		if(!((fl >> m) & 1)) continue;
+		const uint32_t len = a.b.len[m][unit];
+		if(len == 0) continue;
+		const int r = u.n_mates++;
+		const size_t t0 = ((size_t)unit * a.b.n_mates + m) * 2;
+		u.L[r][0] = a.hits + t0 * a.cap;       u.n[r][0] = min(a.nhits[t0], a.cap);
+		u.L[r][1] = a.hits + (t0 + 1) * a.cap; u.n[r][1] = min(a.nhits[t0 + 1], a.cap);
+		u.rdlen[r] = len; fw[r] = a.b.bases + a.b.off[m][unit];
+	}
+	return u.n_mates > 0;
+}
+
+__global__ void __launch_bounds__(128) k_prep(const UnitArgs a) {
+	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
+	if(unit >= a.b.n_units) return;
+	UnitHits u; const uint8_t* fw[2];
+	uint32_t rows = 0;
+	if(load_unit(a, unit, u, fw)) {
+		Counters local; Counters* lc = nullptr;
+		if(a.ctr) { memset(&local, 0, sizeof local); lc = &local; }
+		for(int r = 0; r < u.n_mates; r++) post_search(a.v, a.p, fw[r], u.rdlen[r], u.L[r][0], u.n[r][0], u.L[r][1], u.n[r][1], lc);
+		SortAndCount sc(a.p, u);
+		for_each_visit(a.p, u, sc);
+		rows = (uint32_t)(sc.rows > 0xFFFFFFFFull ? 0xFFFFFFFFull : sc.rows);
+		if(lc) {
+			atomicAdd(&a.ctr->units, 1ull);
+			if(local.ext_searches) {
+				atomicAdd(&a.ctr->ext_searches, local.ext_searches); atomicAdd(&a.ctr->partial_searches, local.partial_searches);
+				atomicAdd(&a.ctr->ftab_probes, local.ftab_probes); atomicAdd(&a.ctr->sides_search, local.sides_search); atomicAdd(&a.ctr->lf_steps, local.lf_steps);
+			}
+		}
+	}
+	a.nrows[unit] = rows;
+}
+
+__global__ void __launch_bounds__(128) k_rows(const UnitArgs a) {
+	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
+	if(unit >= a.b.n_units) return;
+	const uint64_t off = a.row_off[unit], n = a.row_off[unit + 1] - off;
+	if(n == 0) return;
+	if(off + n > a.rows_cap) { atomicExch(a.overflow, 2u); return; }
+	UnitHits u; const uint8_t* fw[2];
+	if(!load_unit(a, unit, u, fw)) return;
+	EmitRows er(a.p, u, a.rows + off);
+	for_each_visit(a.p, u, er);
+}
+
+__global__ void __launch_bounds__(128) k_score(const UnitArgs a) {
+	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
+	if(unit >= a.b.n_units) return;
+	uint32_t no = 0;
+	const uint64_t off = a.row_off[unit], n = a.row_off[unit + 1] - off;
+	if(n > 0 && off + n <= a.rows_cap) {
+		UnitHits u; const uint8_t* fw[2];
+		if(load_unit(a, unit, u, fw)) {
+			ScoreVisit sv(a.v, a.p, u, a.ids + off, a.entries + off);
+			for_each_visit(a.p, u, sv);
+			no = reduce_and_emit(a.v, a.p, u.n_mates == 2, a.entries + off, sv.nmap, a.tcs + off, a.recs_sparse + off);
+		}
+	}
+	a.nout[unit] = no;
+}
+
+// =======================================================================================
+// scan (u32 -> exclusive u64, n+1 outputs) : 3 small kernels, 1024 elements per block
+// =======================================================================================
+static const int kScanBlock = 256, kScanPer = 4;   // 1024 per block
+
+__global__ void __launch_bounds__(kScanBlock) k_scan_sums(const uint32_t* in, uint64_t n, uint64_t* bsum) {
+	__shared__ uint64_t sh[kScanBlock];
+	const uint64_t base = (uint64_t)blockIdx.x * kScanBlock * kScanPer + (uint64_t)threadIdx.x * kScanPer;
+	uint64_t s = 0;
+	for(int i = 0; i < kScanPer; i++) if(base + i < n) s += in[base + i];
+	sh[threadIdx.x] = s; __syncthreads();
+	for(int d = kScanBlock / 2; d > 0; d >>= 1) { if((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d]; __syncthreads(); }
+	if(threadIdx.x == 0) bsum[blockIdx.x] = sh[0];
+}
+__global__ void k_scan_top(uint64_t* bsum, uint64_t nb, uint64_t* total) {   // single thread block, serial over blocks by chunks
+	__shared__ uint64_t carry;
+	__shared__ uint64_t sh[1024];
+	if(threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for(uint64_t base = 0; base < nb; base += 1024) {
+		const uint64_t i = base + threadIdx.x;
+		const uint64_t vv = i < nb ? bsum[i] : 0;
+		sh[threadIdx.x] = vv; __syncthreads();
+		for(int d = 1; d < 1024; d <<= 1) { uint64_t t = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : 0; __syncthreads(); sh[threadIdx.x] += t; __syncthreads(); }
+		if(i < nb) bsum[i] = carry + sh[threadIdx.x] - vv;
+		__syncthreads();
+		if(threadIdx.x == 1023) carry += sh[1023];
+		__syncthreads();
+	}
+	if(threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(kScanBlock) k_scan_apply(const uint32_t* in, uint64_t n, const uint64_t* bsum, const uint64_t* total, uint64_t* out) {
+	__shared__ uint64_t sh[kScanBlock];
+	const uint64_t base = (uint64_t)blockIdx.x * kScanBlock * kScanPer + (uint64_t)threadIdx.x * kScanPer;
+	uint32_t vals[kScanPer]; uint64_t s = 0;
+	for(int i = 0; i < kScanPer; i++) { vals[i] = base + i < n ? in[base + i] : 0; s += vals[i]; }
+	sh[threadIdx.x] = s; __syncthreads();
+	for(int d = 1; d < kScanBlock; d <<= 1) { uint64_t t = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : 0; __syncthreads(); sh[threadIdx.x] += t; __syncthreads(); }
+	uint64_t run = bsum[blockIdx.x] + sh[threadIdx.x] - s;
+	for(int i = 0; i < kScanPer; i++) { if(base + i < n) out[base + i] = run; run += vals[i]; }
+	if(blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
+}
+
+// =======================================================================================
+// k_resolve : group of 8 lanes per SA row
+// =======================================================================================
+enum { R_DONE = 0, R_WALK = 1, R_SAMPLE = 2 };
+struct ResolveArgs {
+	IndexView v; const uint64_t* rows; uint32_t* ids; const uint64_t* total; uint64_t rows_cap;
+	unsigned long long* task_ctr; uint32_t chunk; Counters* ctr;
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kSearchThreads) k_resolve(const ResolveArgs a) {
+	const unsigned lane = threadIdx.x & 31, gl = lane & 7, gbase = lane & 24, gmask = 0xFFu << gbase;
+	const uint4* sides4 = reinterpret_cast<const uint4*>(a.v.sides);
+	uint64_t n = *a.total; if(n > a.rows_cap) n = a.rows_cap;
+	const uint64_t lowmask = ((uint64_t)1 << a.v.off_rate) - 1;
+	uint64_t tnext = 0, tend = 0, idx = 0, row = 0;
+	int mode = R_DONE;
+	unsigned long long c_walk = 0, c_rows = 0;
+
+	// classify `row` without memory: returns next mode; writes result for '$'
+	auto settle = [&](uint64_t r) -> int {
+		if(r == a.v.zoff) { if(gl == 0) a.ids[idx] = 0; return R_DONE; }
+		if((r & lowmask) == 0) return R_SAMPLE;
+		return R_WALK;
+	};
+	auto next_row = [&]() -> bool {       // loops until a row needs memory; false when out of work
+		for(;;) {
+			if(tnext >= tend) {
+				unsigned long long base = 0;
+				if(gl == 0) base = atomicAdd(a.task_ctr, (unsigned long long)a.chunk);
+				base = __shfl_sync(gmask, base, gbase);
+				if(base >= n) { mode = R_DONE; return false; }
+				tnext = base; tend = base + a.chunk < n ? base + a.chunk : n;
+			}
+			idx = tnext++; row = a.rows[idx];
+			if(COUNT) c_rows++;
+			mode = settle(row);
+			if(mode != R_DONE) return true;
+		}
+	};
+	next_row();
+	while(__any_sync(0xffffffffu, mode != R_DONE)) {
+		// ---------------- single fetch point ----------------
+		uint4 da = make_uint4(0, 0, 0, 0); uint32_t bits = 0, samp = 0;
+		uint64_t s = 0; uint32_t off = 0; bool chk = false;
+		if(mode == R_WALK) {
+			s = row / 384; off = (uint32_t)(row - s * 384);
+			da = __ldg(sides4 + s * 8 + gl);
+			chk = a.v.n_boundaries && a.v.last_boundary > 0 && row <= a.v.last_boundary;
+			if(chk) bits = __ldg(a.v.bbits + ((row >> a.v.bshift) >> 5));
+		} else if(mode == R_SAMPLE) {
+			if(gl == 0) samp = a.v.sample32 ? __ldg(a.v.sample32 + (row >> a.v.off_rate)) : (uint32_t)__ldg(a.v.sample16 + (row >> a.v.off_rate));
+		}
+		// ---------------- consume ----------------
+		if(mode == R_SAMPLE) {
+			if(gl == 0) a.ids[idx] = samp;
+			next_row();
+		} else if(mode == R_WALK) {
+			bool found = false;
+			if(chk && (bits >> ((row >> a.v.bshift) & 31)) & 1u) {   // rare: binary search of the boundary rows
+				uint32_t lo = 0, hi = a.v.n_boundaries;
+				while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(a.v.brow[mid] < row) lo = mid + 1; else hi = mid; }
+				if(lo < a.v.n_boundaries && a.v.brow[lo] == row) {
+					found = true;
+					if(gl == 0) a.ids[idx] = a.v.sample32 ? a.v.bseq[lo] : (uint32_t)(uint16_t)a.v.bseq[lo];
+				}
+			}
+			if(found) next_row();
+			else {
+				const int c = group_char(da, off, gmask, gbase);
+				const uint32_t rep = (uint32_t)c * 0x55555555u;
+				int nn = (int)off - 64 * (int)gl; nn = nn < 0 ? 0 : (nn > 64 ? 64 : nn);
+				uint32_t cnt = gl < 6 ? lane_count(da, rep, nn) : 0u;
+				cnt = group_sum(cnt, gmask);
+				const uint64_t occ = group_occ(da, c, gmask, gbase);
+				uint64_t r = cnt;
+				if(c == 0 && s == a.v.zside && a.v.zoffc < off) r--;
+				row = a.v.fchr[c] + occ + r;
+				if(COUNT) c_walk++;
+				mode = settle(row);
+				if(mode == R_DONE) next_row();
+			}
+		}
+	}
+	if(COUNT && gl == 0 && a.ctr) { atomicAdd(&a.ctr->walk_steps, c_walk); atomicAdd(&a.ctr->rows_resolved, c_rows); }
+}
+
+// =======================================================================================
+// k_compact
+// =======================================================================================
+__global__ void __launch_bounds__(128) k_compact(uint32_t n_units, const uint64_t* row_off, const uint64_t* out_off,
+                                                 const OutRec* sparse, OutRec* dense, uint32_t* rec_off32, uint64_t dense_cap, unsigned int* overflow) {
+	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
+	if(unit > n_units) return;
+	if(unit == n_units) { rec_off32[unit] = (uint32_t)out_off[unit]; return; }
+	const uint64_t o = out_off[unit], n = out_off[unit + 1] - o;
+	rec_off32[unit] = (uint32_t)o;
+	if(o + n > dense_cap) { if(n) atomicExch(overflow, 3u); return; }
+	const uint64_t src = row_off[unit];
+	for(uint64_t i = 0; i < n; i++) dense[o + i] = sparse[src + i];
+}
+
+// =======================================================================================
+// test hook kernels
+// =======================================================================================
+__global__ void k_test_lf(IndexView v, const uint64_t* rows, const uint8_t* chars, uint64_t n, uint64_t* out) {
+	const unsigned lane = threadIdx.x & 31, gl = lane & 7, gbase = lane & 24, gmask = 0xFFu << gbase;
+	const uint4* sides4 = reinterpret_cast<const uint4*>(v.sides);
+	const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+	const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
+	const uint64_t iters = (n + ngroups - 1) / ngroups;          // uniform trip count: all groups of a warp stay in lockstep
+	for(uint64_t it = 0; it < iters; it++) {
+		const uint64_t i = g + it * ngroups;
+		const bool act = i < n;
+		const uint64_t row = act ? rows[i] : 0;
+		const uint64_t s = row / 384; const uint32_t off = (uint32_t)(row - s * 384);
+		const uint4 da = __ldg(sides4 + s * 8 + gl);
+		int c = act ? chars[i] : 0;
+		const int rowc = group_char(da, off, gmask, gbase);
+		if(c > 3) c = rowc;
+		const uint32_t rep = (uint32_t)c * 0x55555555u;
+		int nn = (int)off - 64 * (int)gl; nn = nn < 0 ? 0 : (nn > 64 ? 64 : nn);
+		uint32_t cnt = gl < 6 ? lane_count(da, rep, nn) : 0u;
+		cnt = group_sum(cnt, gmask);
+		const uint64_t occ = group_occ(da, c, gmask, gbase);
+		uint64_t r = cnt;
+		if(c == 0 && s == v.zside && v.zoffc < off) r--;
+		if(act && gl == 0) out[i] = v.fchr[c] + occ + r;
+	}
+}
+
+// =======================================================================================
+// host side: index replica, contexts, batches
+// =======================================================================================
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+	va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(CFB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while(0)
+
+extern "C" const char* cfb_last_error(void) { return g_err; }
+extern "C" const char* cfb_version(void) { return "cfb200 0.1 (sm_100a)"; }
+
+template <class T> struct DBuf {     // growable device buffer
+	T* p = nullptr; size_t cap = 0;
+	cudaError_t ensure(size_t n) {
+		if(n <= cap) return cudaSuccess;
+		if(p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = n + n / 8 + 16;
+		cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+		if(e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T> struct HBuf {     // growable pinned host buffer
+	T* p = nullptr; size_t cap = 0;
+	cudaError_t ensure(size_t n) {
+		if(n <= cap) return cudaSuccess;
+		if(p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = n + n / 8 + 16;
+		cudaError_t e = cudaMallocHost((void**)&p, want * sizeof(T));
+		if(e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if(p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct cfb_index {
+	HostIndex h;
+	int device = -1;
+	IndexView view;            // device pointers (taxonomy-independent part)
+	std::vector<void*> dptrs;
+	uint64_t device_bytes = 0;
+	int sm_count = 0;
+};
+
+static int upload(cfb_index* ix, const void* src, size_t bytes, const void** dst) {
+	void* d = nullptr;
+	CK(cudaMalloc(&d, bytes ? bytes : 16));
+	if(bytes) CK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+	ix->dptrs.push_back(d); ix->device_bytes += bytes;
+	*dst = d;
+	return CFB_OK;
+}
+
+extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out) {
+	if(!basename || !out) return fail(CFB_EINVAL, "cfb_index_load: null argument");
+	cfb_index* ix = new cfb_index();
+	std::string err = load_cf_index(basename, ix->h);
+	if(!err.empty()) { delete ix; return fail(CFB_EIO, "%s", err.c_str()); }
+	const HostIndex& h = ix->h;
+	ix->device = device;
+	if(device >= 0) {
+		if(h.line_rate != 7) { const int lr = h.line_rate; delete ix; return fail(CFB_EFORMAT, "index lineRate %d unsupported: the sm_100a kernels require 128-byte sides (centrifuge-build default --linerate 7)", lr); }
+		if(h.ftab_chars > 15) { const int fc = h.ftab_chars; delete ix; return fail(CFB_EFORMAT, "ftabChars %d unsupported", fc); }
+		int ndev = 0;
+		if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) { delete ix; return fail(CFB_ENODEV, "no CUDA device %d (found %d); this library has no CPU fallback", device, ndev); }
+		cudaDeviceProp prop;
+		if(cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ix; return fail(CFB_ENODEV, "cannot use CUDA device %d", device); }
+		ix->sm_count = prop.multiProcessorCount;
+		IndexView& v = ix->view; memset(&v, 0, sizeof v);
+		int rc;
+		#define UP(field, vec, T) if((rc = upload(ix, (vec).data(), (vec).size() * sizeof(T), (const void**)&v.field)) != CFB_OK) { cfb_index_free(ix); return rc; }
+		UP(sides, h.sides, uint8_t) UP(ftab, h.ftab, uint64_t) UP(eftab, h.eftab, uint64_t)
+		if(h.wide_sample) { UP(sample32, h.sample32, uint32_t) } else { UP(sample16, h.sample16, uint16_t) }
+		UP(brow, h.brow, uint64_t) UP(bseq, h.bseq, uint32_t) UP(bbits, h.bbits, uint32_t)
+		UP(seq_taxid, h.seq_taxid, uint64_t) UP(seq_path, h.seq_path, int32_t) UP(paths, h.paths, uint64_t)
+		#undef UP
+		v.len = h.len; v.zoff = h.zoff; v.zside = h.zoff / 384; v.zoffc = (uint32_t)(h.zoff % 384);
+		for(int i = 0; i < 4; i++) v.fchr[i] = h.fchr[i];
+		v.last_boundary = h.last_boundary; v.num_sides = h.num_sides;
+		v.n_boundaries = (uint32_t)h.brow.size(); v.n_seqs = (uint32_t)h.seq_taxid.size();
+		v.off_rate = h.off_rate; v.ftab_chars = h.ftab_chars; v.bshift = h.bshift;
+		// host copies of the big arrays are no longer needed once uploaded
+		std::vector<uint8_t>().swap(ix->h.sides);
+	}
+	*out = ix;
+	return CFB_OK;
+}
+extern "C" void cfb_index_free(cfb_index* ix) {
+	if(!ix) return;
+	if(ix->device >= 0) { cudaSetDevice(ix->device); for(size_t i = 0; i < ix->dptrs.size(); i++) cudaFree(ix->dptrs[i]); }
+	delete ix;
+}
+extern "C" int cfb_index_get_info(const cfb_index* ix, cfb_index_info* o) {
+	if(!ix || !o) return fail(CFB_EINVAL, "null argument");
+	const HostIndex& h = ix->h;
+	o->len = h.len; o->num_sides = h.num_sides; o->n_seqs = h.seq_taxid.size(); o->n_tax_nodes = h.nodes.size();
+	o->n_boundaries = h.brow.size(); o->line_rate = h.line_rate; o->off_rate = h.off_rate; o->ftab_chars = h.ftab_chars;
+	o->sample_bytes = h.wide_sample ? 4 : 2; o->compressed = h.compressed ? 1 : 0; o->device = ix->device; o->device_bytes = ix->device_bytes;
+	return CFB_OK;
+}
+extern "C" const char* cfb_index_seq_name(const cfb_index* ix, uint32_t s) { return (ix && s < ix->h.seq_name.size()) ? ix->h.seq_name[s].c_str() : NULL; }
+extern "C" uint64_t cfb_index_seq_taxid(const cfb_index* ix, uint32_t s) { return (ix && s < ix->h.seq_taxid.size()) ? ix->h.seq_taxid[s] : 0; }
+extern "C" int cfb_index_tax_node(const cfb_index* ix, uint64_t taxid, uint64_t* parent, int* rank, int* leaf) {
+	const TaxNode* n = ix ? ix->h.find_node(taxid) : NULL;
+	if(!n) return 0;
+	if(parent) *parent = n->parent; if(rank) *rank = n->rank; if(leaf) *leaf = n->leaf;
+	return 1;
+}
+extern "C" void cfb_params_default(cfb_params* p) {
+	if(!p) return;
+	memset(p, 0, sizeof *p); p->khits = 5; p->min_hitlen = 22; p->tree_traverse = 1; p->class_rank_slot = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+static const int kSlots = 3;
+
+struct Slot {
+	cudaStream_t st = nullptr;
+	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	// inputs
+	HBuf<uint8_t> h_bases; HBuf<uint64_t> h_off; HBuf<uint32_t> h_len; HBuf<uint8_t> h_flags;
+	DBuf<uint8_t> d_bases; DBuf<uint64_t> d_off; DBuf<uint32_t> d_len; DBuf<uint8_t> d_flags;
+	// work
+	DBuf<HitRec> hits; DBuf<uint32_t> nhits; DBuf<uint32_t> nrows; DBuf<uint64_t> row_off; DBuf<uint64_t> bsum;
+	DBuf<uint64_t> rows; DBuf<uint32_t> ids; DBuf<Entry> entries; DBuf<TaxCnt> tcs; DBuf<OutRec> sparse;
+	DBuf<uint32_t> nout; DBuf<uint64_t> out_off; DBuf<OutRec> dense; DBuf<uint32_t> rec_off32;
+	DBuf<unsigned long long> scal;    // [0] search task ctr (u32 used), [1] resolve ctr, [2] overflow, [3] total rows, [4] total recs
+	HBuf<unsigned long long> h_scal;
+	HBuf<OutRec> h_recs; HBuf<uint32_t> h_rec_off;
+	// batch bookkeeping
+	BatchView bv; uint64_t n_units = 0, n_bases = 0; uint32_t maxlen = 0, cap = 0; uint64_t rows_cap = 0, dense_cap = 0;
+	bool pending = false;
+	void release() {
+		h_bases.release(); h_off.release(); h_len.release(); h_flags.release(); d_bases.release(); d_off.release(); d_len.release(); d_flags.release();
+		hits.release(); nhits.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
+		sparse.release(); nout.release(); out_off.release(); dense.release(); rec_off32.release(); scal.release(); h_scal.release(); h_recs.release(); h_rec_off.release();
+		for(int i = 0; i < 6; i++) if(ev[i]) cudaEventDestroy(ev[i]);
+		if(st) cudaStreamDestroy(st);
+	}
+};
+
+struct cfb_dbatch { int slot; };
+
+struct cfb_ctx {
+	const cfb_index* ix = nullptr;
+	IndexView view; Params prm;
+	DBuf<uint8_t> d_excl; DBuf<uint64_t> d_host;
+	Slot slots[kSlots];
+	Counters* d_ctr = nullptr; bool count = false;
+	uint64_t launches = 0;
+	int search_blocks = 0, resolve_blocks = 0;
+	cfb_dbatch resident; bool resident_used = false;
+};
+
+// every tree node whose ancestor chain contains a listed id (Classifier ctor classifier.h:157-201)
+static void expand_taxids(const HostIndex& h, const uint64_t* ids, uint64_t n, std::set<uint64_t>& out) {
+	if(n == 0 || !ids) return;
+	for(size_t i = 0; i < h.nodes.size(); i++) {
+		uint64_t t = h.nodes[i].taxid;
+		for(;;) {
+			bool found = false;
+			for(uint64_t k = 0; k < n; k++) if(ids[k] == t) { found = true; break; }
+			if(found) { out.insert(h.nodes[i].taxid); break; }
+			const TaxNode* nd = h.find_node(t);
+			if(!nd || nd->parent == t) break;
+			t = nd->parent;
+		}
+	}
+}
+
+extern "C" void cfb_ctx_destroy(cfb_ctx* c) {
+	if(!c) return;
+	if(c->ix && c->ix->device >= 0) cudaSetDevice(c->ix->device);
+	for(int i = 0; i < kSlots; i++) c->slots[i].release();
+	c->d_excl.release(); c->d_host.release();
+	if(c->d_ctr) cudaFree(c->d_ctr);
+	delete c;
+}
+
+extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx** out) {
+	if(!ix || !p || !out) return fail(CFB_EINVAL, "cfb_ctx_create: null argument");
+	if(ix->device < 0) return fail(CFB_ENODEV, "index was loaded host-only; classification needs a CUDA device (no CPU fallback)");
+	if(p->khits < 1) return fail(CFB_EINVAL, "khits must be >= 1");
+	CK(cudaSetDevice(ix->device));
+	cfb_ctx* c = new cfb_ctx();
+	c->ix = ix; c->view = ix->view;
+	const HostIndex& h = ix->h;
+	Params& q = c->prm;
+	q.khits = (uint32_t)p->khits;
+	q.min_hitlen = (uint32_t)(p->min_hitlen < 15 ? 15 : p->min_hitlen);
+	q.ihits = (uint32_t)std::max(p->khits, 5) * (h.compressed ? 4u : 40u);       // ReportingParams aln_sink.h:580-588
+	q.increment = (2 * q.min_hitlen <= 33) ? 10 : (2 * q.min_hitlen - 33);        // classifier.h:226
+	q.tree_traverse = p->tree_traverse ? 1 : 0;
+	q.class_rank_slot = (uint32_t)(p->class_rank_slot & 0xff);
+	std::set<uint64_t> host, excl;
+	expand_taxids(h, p->host_taxids, p->n_host_taxids, host);
+	expand_taxids(h, p->excluded_taxids, p->n_excluded_taxids, excl);
+	#define CKC(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { cfb_ctx_destroy(c); return fail(CFB_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while(0)
+	if(!excl.empty()) {
+		std::vector<uint8_t> fl(h.seq_taxid.size(), 0);
+		for(size_t i = 0; i < fl.size(); i++) fl[i] = excl.count(h.seq_taxid[i]) ? 1 : 0;
+		CKC(c->d_excl.ensure(fl.size())); CKC(cudaMemcpy(c->d_excl.p, fl.data(), fl.size(), cudaMemcpyHostToDevice));
+		c->view.seq_excluded = c->d_excl.p;
+	}
+	if(!host.empty()) {
+		std::vector<uint64_t> hv(host.begin(), host.end());
+		CKC(c->d_host.ensure(hv.size())); CKC(cudaMemcpy(c->d_host.p, hv.data(), hv.size() * 8, cudaMemcpyHostToDevice));
+		c->view.host_taxids = c->d_host.p; c->view.n_host = (uint32_t)hv.size();
+	}
+	for(int i = 0; i < kSlots; i++) {
+		CKC(cudaStreamCreateWithFlags(&c->slots[i].st, cudaStreamNonBlocking));
+		for(int e = 0; e < 6; e++) CKC(cudaEventCreate(&c->slots[i].ev[e]));
+		CKC(c->slots[i].scal.ensure(8)); CKC(c->slots[i].h_scal.ensure(8));
+	}
+	CKC(cudaMalloc((void**)&c->d_ctr, sizeof(Counters))); CKC(cudaMemset(c->d_ctr, 0, sizeof(Counters)));
+	int occ = 0;
+	CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<false>, kSearchThreads, 0));
+	c->search_blocks = ix->sm_count * std::max(occ, 1);
+	CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
+	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
+	const char* cnt = getenv("CFB_COUNT");
+	c->count = cnt && cnt[0] == '1';
+	#undef CKC
+	*out = c;
+	return CFB_OK;
+}
+extern "C" int cfb_ctx_slots(const cfb_ctx*) { return kSlots - 1; }   // last slot is reserved for resident batches
+extern "C" int cfb_ctx_kernel_launches(const cfb_ctx* c, uint64_t* n) { if(!c || !n) return CFB_EINVAL; *n = c->launches; return CFB_OK; }
+
+// Validate + stage a batch into the slot's pinned buffers and enqueue H2D copies.
+static int stage_batch(cfb_ctx* c, Slot& s, const cfb_batch* b) {
+	if(!b || b->n_mates < 1 || b->n_mates > 2 || !b->bases || !b->off[0] || !b->len[0] || (b->n_mates == 2 && (!b->off[1] || !b->len[1])))
+		return fail(CFB_EINVAL, "malformed cfb_batch");
+	if(b->n_units >= (1ull << 30)) return fail(CFB_EINVAL, "batch too large (n_units must be < 2^30)");
+	const uint64_t n = b->n_units; const int nm = b->n_mates;
+	uint32_t maxlen = 0;
+	for(int m = 0; m < nm; m++) for(uint64_t i = 0; i < n; i++) {
+		if(b->off[m][i] + b->len[m][i] > b->n_bases) return fail(CFB_EINVAL, "unit %llu mate %d exceeds n_bases", (unsigned long long)i, m + 1);
+		maxlen = std::max(maxlen, b->len[m][i]);
+	}
+	if(maxlen > 60000) return fail(CFB_EINVAL, "read longer than 60000 bases");
+	CK(s.h_bases.ensure(b->n_bases)); CK(s.h_off.ensure(n * nm)); CK(s.h_len.ensure(n * nm)); CK(s.h_flags.ensure(n));
+	CK(s.d_bases.ensure(b->n_bases + 16)); CK(s.d_off.ensure(n * nm)); CK(s.d_len.ensure(n * nm)); CK(s.d_flags.ensure(n));
+	memcpy(s.h_bases.p, b->bases, b->n_bases);
+	for(int m = 0; m < nm; m++) { memcpy(s.h_off.p + m * n, b->off[m], n * 8); memcpy(s.h_len.p + m * n, b->len[m], n * 4); }
+	if(b->flags) memcpy(s.h_flags.p, b->flags, n); else memset(s.h_flags.p, 3, n);
+	CK(cudaMemcpyAsync(s.d_bases.p, s.h_bases.p, b->n_bases, cudaMemcpyHostToDevice, s.st));
+	CK(cudaMemcpyAsync(s.d_off.p, s.h_off.p, n * nm * 8, cudaMemcpyHostToDevice, s.st));
+	CK(cudaMemcpyAsync(s.d_len.p, s.h_len.p, n * nm * 4, cudaMemcpyHostToDevice, s.st));
+	CK(cudaMemcpyAsync(s.d_flags.p, s.h_flags.p, n, cudaMemcpyHostToDevice, s.st));
+	s.bv.bases = s.d_bases.p; s.bv.flags = s.d_flags.p; s.bv.n_units = (uint32_t)n; s.bv.n_mates = nm;
+	for(int m = 0; m < 2; m++) { s.bv.off[m] = m < nm ? s.d_off.p + m * n : nullptr; s.bv.len[m] = m < nm ? s.d_len.p + m * n : nullptr; }
+	s.n_units = n; s.n_bases = b->n_bases; s.maxlen = maxlen;
+	(void)c;
+	return CFB_OK;
+}
+
+// Enqueue all kernels of one batch on the slot's stream.  stage: 0 = from search, 1 = from k_rows
+// (after a rows-capacity overflow; the hit lists are already post-processed and sorted).
+static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
+	const uint64_t n = s.n_units; const int nm = s.bv.n_mates;
+	const uint64_t ntasks = n * nm * 2;
+	const uint32_t ublocks = (uint32_t)((n + 127) / 128);
+	const uint64_t scan_blocks = (n + kScanBlock * kScanPer - 1) / (kScanBlock * kScanPer);
+	if(n == 0) return CFB_OK;
+	if(stage == 0) {
+		if(s.cap == 0) s.cap = s.maxlen / 4 + 8;      // >= #Ns allowed by the N filter (0.15 len) + len/10 + slack
+		CK(s.hits.ensure(ntasks * s.cap)); CK(s.nhits.ensure(ntasks)); CK(s.nrows.ensure(n)); CK(s.row_off.ensure(n + 1));
+		CK(s.bsum.ensure(scan_blocks + 1)); CK(s.nout.ensure(n)); CK(s.out_off.ensure(n + 1)); CK(s.rec_off32.ensure(n + 1));
+		s.rows_cap = std::max<uint64_t>(s.rows_cap, std::max<uint64_t>(n * 12, 4096));
+	}
+	CK(s.rows.ensure(s.rows_cap)); CK(s.ids.ensure(s.rows_cap)); CK(s.entries.ensure(s.rows_cap)); CK(s.tcs.ensure(s.rows_cap)); CK(s.sparse.ensure(s.rows_cap));
+	s.dense_cap = s.rows_cap; CK(s.dense.ensure(s.dense_cap));
+	CK(cudaMemsetAsync(s.scal.p, 0, 3 * sizeof(unsigned long long), s.st));   // task counters + overflow flag; [3],[4] are rewritten by the scans
+	if(time_it) CK(cudaEventRecord(s.ev[0], s.st));
+	Counters* ctr = c->count ? c->d_ctr : nullptr;
+	if(c->count && stage == 0) CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), s.st));
+	UnitArgs ua; ua.v = c->view; ua.p = c->prm; ua.b = s.bv; ua.hits = s.hits.p; ua.nhits = s.nhits.p; ua.cap = s.cap;
+	ua.nrows = s.nrows.p; ua.row_off = s.row_off.p; ua.rows = s.rows.p; ua.ids = s.ids.p; ua.rows_cap = s.rows_cap;
+	ua.entries = s.entries.p; ua.tcs = s.tcs.p; ua.recs_sparse = s.sparse.p; ua.nout = s.nout.p;
+	ua.overflow = (unsigned int*)(s.scal.p + 2); ua.ctr = ctr;
+	if(stage == 0) {
+		SearchArgs sa; sa.v = c->view; sa.p = c->prm; sa.b = s.bv; sa.hits = s.hits.p; sa.nhits = s.nhits.p; sa.cap = s.cap;
+		sa.task_ctr = (unsigned int*)(s.scal.p + 0); sa.ntasks = (uint32_t)ntasks; sa.overflow = (unsigned int*)(s.scal.p + 2); sa.ctr = ctr;
+		const uint64_t groups = (uint64_t)c->search_blocks * (kSearchThreads / kGroup);
+		uint64_t chunk = ntasks / (groups * 8); sa.chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(chunk, 1), 16);
+		const int blocks = (int)std::min<uint64_t>((uint64_t)c->search_blocks, (ntasks + kSearchThreads / kGroup - 1) / (kSearchThreads / kGroup));
+		if(c->count) k_search<true><<<blocks, kSearchThreads, 0, s.st>>>(sa); else k_search<false><<<blocks, kSearchThreads, 0, s.st>>>(sa);
+		c->launches++;
+		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
+		k_prep<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
+		k_scan_sums<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nrows.p, n, s.bsum.p);
+		k_scan_top<<<1, 1024, 0, s.st>>>(s.bsum.p, scan_blocks, (uint64_t*)(s.scal.p + 3));
+		k_scan_apply<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nrows.p, n, s.bsum.p, (const uint64_t*)(s.scal.p + 3), s.row_off.p);
+		c->launches += 3;
+	} else if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
+	k_rows<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
+	if(time_it) CK(cudaEventRecord(s.ev[2], s.st));
+	ResolveArgs ra; ra.v = c->view; ra.rows = s.rows.p; ra.ids = s.ids.p; ra.total = (const uint64_t*)(s.scal.p + 3); ra.rows_cap = s.rows_cap;
+	ra.task_ctr = s.scal.p + 1; ra.chunk = 4; ra.ctr = ctr;
+	if(c->count) k_resolve<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra);
+	c->launches++;
+	if(time_it) CK(cudaEventRecord(s.ev[3], s.st));
+	k_score<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
+	k_scan_sums<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nout.p, n, s.bsum.p);
+	k_scan_top<<<1, 1024, 0, s.st>>>(s.bsum.p, scan_blocks, (uint64_t*)(s.scal.p + 4));
+	k_scan_apply<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nout.p, n, s.bsum.p, (const uint64_t*)(s.scal.p + 4), s.out_off.p);
+	k_compact<<<(unsigned)((n + 1 + 127) / 128), 128, 0, s.st>>>((uint32_t)n, s.row_off.p, s.out_off.p, s.sparse.p, s.dense.p, s.rec_off32.p, s.dense_cap, (unsigned int*)(s.scal.p + 2));
+	c->launches += 4;
+	if(time_it) CK(cudaEventRecord(s.ev[4], s.st));
+	CK(cudaMemcpyAsync(s.h_scal.p, s.scal.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.st));
+	CK(cudaGetLastError());
+	return CFB_OK;
+}
+
+// Wait for the kernels, handle capacity overflows by re-running the affected stages, then D2H.
+static int finish_batch(cfb_ctx* c, Slot& s, bool time_it, bool to_host, cfb_result* out) {
+	if(s.n_units == 0) { if(out) { out->n_units = 0; out->n_recs = 0; out->rec_off = nullptr; out->recs = nullptr; } return CFB_OK; }
+	for(int attempt = 0; attempt < 8; attempt++) {
+		CK(cudaStreamSynchronize(s.st));
+		const unsigned ovf = (unsigned)(s.h_scal.p[2] & 0xffffffffu);
+		const uint64_t total_rows = s.h_scal.p[3];
+		if(ovf == 1) {            // hit-list capacity: only possible when the caller's flags bypass the N filter
+			s.cap = s.maxlen + 2;
+			int rc = enqueue_kernels(c, s, 0, time_it); if(rc) return rc;
+			continue;
+		}
+		if(total_rows > s.rows_cap) {
+			s.rows_cap = total_rows + total_rows / 4 + 1024;
+			int rc = enqueue_kernels(c, s, 1, time_it); if(rc) return rc;
+			continue;
+		}
+		if(ovf != 0) return fail(CFB_ECUDA, "internal capacity error %u", ovf);
+		break;
+	}
+	const uint64_t nrec = s.h_scal.p[4];
+	if(to_host) {
+		CK(s.h_recs.ensure(nrec + 1)); CK(s.h_rec_off.ensure(s.n_units + 1));
+		CK(cudaMemcpyAsync(s.h_rec_off.p, s.rec_off32.p, (s.n_units + 1) * 4, cudaMemcpyDeviceToHost, s.st));
+		if(nrec) CK(cudaMemcpyAsync(s.h_recs.p, s.dense.p, nrec * sizeof(OutRec), cudaMemcpyDeviceToHost, s.st));
+		CK(cudaStreamSynchronize(s.st));
+	}
+	if(out) { out->n_units = s.n_units; out->n_recs = nrec; out->rec_off = s.h_rec_off.p; out->recs = reinterpret_cast<const cfb_rec*>(s.h_recs.p); }
+	return CFB_OK;
+}
+
+extern "C" int cfb_classify_submit(cfb_ctx* c, int slot, const cfb_batch* b) {
+	if(!c || slot < 0 || slot >= kSlots - 1) return fail(CFB_EINVAL, "bad ctx/slot");
+	CK(cudaSetDevice(c->ix->device));
+	Slot& s = c->slots[slot];
+	if(s.pending) return fail(CFB_EINVAL, "slot %d still has an un-waited batch", slot);
+	int rc = stage_batch(c, s, b); if(rc) return rc;
+	s.cap = 0;
+	rc = enqueue_kernels(c, s, 0, false); if(rc) return rc;
+	s.pending = true;
+	return CFB_OK;
+}
+extern "C" int cfb_classify_wait(cfb_ctx* c, int slot, cfb_result* out) {
+	if(!c || slot < 0 || slot >= kSlots - 1 || !out) return fail(CFB_EINVAL, "bad ctx/slot");
+	CK(cudaSetDevice(c->ix->device));
+	Slot& s = c->slots[slot];
+	if(!s.pending) return fail(CFB_EINVAL, "slot %d has no submitted batch", slot);
+	s.pending = false;
+	return finish_batch(c, s, false, true, out);
+}
+extern "C" int cfb_classify_batch(cfb_ctx* c, const cfb_batch* b, cfb_result* out) {
+	int rc = cfb_classify_submit(c, 0, b); if(rc) return rc;
+	return cfb_classify_wait(c, 0, out);
+}
+
+extern "C" int cfb_batch_upload(cfb_ctx* c, const cfb_batch* b, cfb_dbatch** out) {
+	if(!c || !out) return fail(CFB_EINVAL, "null argument");
+	if(c->resident_used) return fail(CFB_EINVAL, "only one resident batch per ctx");
+	CK(cudaSetDevice(c->ix->device));
+	Slot& s = c->slots[kSlots - 1];
+	int rc = stage_batch(c, s, b); if(rc) return rc;
+	CK(cudaStreamSynchronize(s.st));
+	s.cap = 0;
+	c->resident.slot = kSlots - 1; c->resident_used = true;
+	*out = &c->resident;
+	return CFB_OK;
+}
+extern "C" void cfb_dbatch_free(cfb_ctx* c, cfb_dbatch*) { if(c) c->resident_used = false; }
+extern "C" int cfb_classify_resident(cfb_ctx* c, cfb_dbatch* d, float* ms, uint64_t* n_recs) {
+	if(!c || !d) return fail(CFB_EINVAL, "null argument");
+	CK(cudaSetDevice(c->ix->device));
+	Slot& s = c->slots[d->slot];
+	int rc = enqueue_kernels(c, s, 0, true); if(rc) return rc;
+	cfb_result r;
+	rc = finish_batch(c, s, true, false, &r); if(rc) return rc;
+	if(n_recs) *n_recs = r.n_recs;
+	if(ms) {
+		CK(cudaEventSynchronize(s.ev[4]));
+		CK(cudaEventElapsedTime(&ms[0], s.ev[0], s.ev[1])); CK(cudaEventElapsedTime(&ms[1], s.ev[1], s.ev[2]));
+		CK(cudaEventElapsedTime(&ms[2], s.ev[2], s.ev[3])); CK(cudaEventElapsedTime(&ms[3], s.ev[3], s.ev[4]));
+		CK(cudaEventElapsedTime(&ms[4], s.ev[0], s.ev[4]));
+	}
+	return CFB_OK;
+}
+extern "C" int cfb_resident_result(cfb_ctx* c, cfb_result* out) {
+	if(!c || !out || !c->resident_used) return fail(CFB_EINVAL, "no resident batch");
+	CK(cudaSetDevice(c->ix->device));
+	Slot& s = c->slots[kSlots - 1];
+	return finish_batch(c, s, false, true, out);
+}
+extern "C" int cfb_ctx_counters(cfb_ctx* c, uint64_t out[8]) {
+	if(!c || !out) return fail(CFB_EINVAL, "null argument");
+	CK(cudaSetDevice(c->ix->device));
+	Counters h; CK(cudaMemcpy(&h, c->d_ctr, sizeof h, cudaMemcpyDeviceToHost));
+	out[0] = h.units; out[1] = h.partial_searches; out[2] = h.ftab_probes; out[3] = h.sides_search;
+	out[4] = h.walk_steps; out[5] = h.rows_resolved; out[6] = h.lf_steps; out[7] = h.ext_searches;
+	return CFB_OK;
+}
+
+extern "C" void* cfb_host_alloc(size_t bytes) { void* p = nullptr; if(cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; return p; }
+extern "C" void cfb_host_free(void* p) { if(p) cudaFreeHost(p); }
+
+extern "C" int cfb_test_lf(const cfb_index* ix, const uint64_t* rows, const uint8_t* chars, uint64_t n, uint64_t* out) {
+	if(!ix || ix->device < 0) return fail(CFB_ENODEV, "no device");
+	CK(cudaSetDevice(ix->device));
+	uint64_t *dr = nullptr, *dout = nullptr; uint8_t* dc = nullptr;
+	CK(cudaMalloc(&dr, n * 8 + 8)); CK(cudaMalloc(&dout, n * 8 + 8)); CK(cudaMalloc(&dc, n + 8));
+	CK(cudaMemcpy(dr, rows, n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dc, chars, n, cudaMemcpyHostToDevice));
+	k_test_lf<<<64, 128>>>(ix->view, dr, dc, n, dout);
+	CK(cudaDeviceSynchronize());
+	CK(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));
+	cudaFree(dr); cudaFree(dout); cudaFree(dc);
+	return CFB_OK;
+}
+extern "C" int cfb_test_resolve(const cfb_index* ix, const uint64_t* rows, uint64_t n, uint32_t* out) {
+	if(!ix || ix->device < 0) return fail(CFB_ENODEV, "no device");
+	CK(cudaSetDevice(ix->device));
+	uint64_t* dr = nullptr; uint32_t* dout = nullptr; unsigned long long* sc = nullptr;
+	CK(cudaMalloc(&dr, n * 8 + 8)); CK(cudaMalloc(&dout, n * 4 + 8)); CK(cudaMalloc(&sc, 16));
+	CK(cudaMemcpy(dr, rows, n * 8, cudaMemcpyHostToDevice));
+	unsigned long long init[2] = {0ull, (unsigned long long)n};
+	CK(cudaMemcpy(sc, init, 16, cudaMemcpyHostToDevice));
+	ResolveArgs ra; ra.v = ix->view; ra.rows = dr; ra.ids = dout; ra.total = (const uint64_t*)(sc + 1); ra.rows_cap = n; ra.task_ctr = sc; ra.chunk = 2; ra.ctr = nullptr;
+	k_resolve<false><<<32, kSearchThreads>>>(ra);
+	CK(cudaDeviceSynchronize());
+	CK(cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost));
+	cudaFree(dr); cudaFree(dout); cudaFree(sc);
+	return CFB_OK;
+}

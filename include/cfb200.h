@@ -1,0 +1,161 @@
+/* include/cfb200.h -- C ABI of the B200-native Centrifuge classification path.
+ *
+ * This is the batch form of the reference's inner operator boundary: one call
+ * classifies a batch of reads/pairs exactly as a sequence of
+ *     Classifier::initRead/initReads (hi_aligner.h:739,765) + Classifier::go (classifier.h:212)
+ * calls would, against the same `.1-.4.cf` index files that Ebwt<uint64_t> loads
+ * (bt2_idx.h:566-854, bt2_io.h:42-685).  The caller is the host worker that replaces
+ * multiseedSearchWorker (centrifuge.cpp:2342); it keeps read parsing, the N filter, the
+ * per-read RNG / selectByScore tie shuffle (aln_sink.h:1861), TSV formatting and
+ * SpeciesMetrics, all of which libcfb200_host provides as well (cfb_run below replaces
+ * `extern "C" int centrifuge(int, const char**)`, centrifuge.cpp:3345).
+ *
+ * Plain C, plain pointers and sizes; nothing throws across this boundary.  All functions
+ * return 0 on success or a negative CFB_E* code; cfb_last_error() gives the message.
+ * There is no CPU fallback: every classify entry point fails with CFB_ENODEV when no
+ * sm_100-class CUDA device is usable.
+ */
+#ifndef CFB200_H_
+#define CFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFB_OK        0
+#define CFB_EINVAL   -1   /* bad argument */
+#define CFB_EIO      -2   /* index / read file problem */
+#define CFB_ENOMEM   -3   /* host or device allocation failed */
+#define CFB_ENODEV   -4   /* no usable CUDA device (no CPU fallback exists) */
+#define CFB_ECUDA    -5   /* CUDA runtime error, see cfb_last_error() */
+#define CFB_EFORMAT  -6   /* index geometry not supported by the kernels */
+
+#define CFB_UID_NONE 0xFFFFFFFFu
+
+typedef struct cfb_index cfb_index;   /* immutable, shareable: host arrays + one device replica */
+typedef struct cfb_ctx   cfb_ctx;     /* per-thread/per-stream work context; not thread-safe */
+
+/* Replaces: Ebwt<index_t> ctor + loadIntoMemory (centrifuge.cpp:2878,2950).
+ * device >= 0 uploads a replica to that GPU; device < 0 loads host tables only
+ * (header / taxonomy inspection; classify calls then fail with CFB_ENODEV). */
+int cfb_index_load(const char* basename, int device, cfb_index** out);
+void cfb_index_free(cfb_index*);
+
+typedef struct {
+	uint64_t len;          /* joined reference length (EbwtParams::_len) */
+	uint64_t num_sides;
+	uint64_t n_seqs;       /* uid_to_tid().size() */
+	uint64_t n_tax_nodes;  /* tree().size() */
+	uint64_t n_boundaries; /* .4.cf entries */
+	int32_t  line_rate, off_rate, ftab_chars;
+	int32_t  sample_bytes; /* 2 or 4 (bt2_io.h:280) */
+	int32_t  compressed;   /* Ebwt::compressed(), bt2_idx.h:661 */
+	int32_t  device;       /* -1 when host-only */
+	uint64_t device_bytes; /* HBM bytes of the replica */
+} cfb_index_info;
+int cfb_index_get_info(const cfb_index*, cfb_index_info* out);
+
+/* Taxonomy accessors the host formatter needs (Ebwt::uid_to_tid/tree/name/size). */
+const char* cfb_index_seq_name(const cfb_index*, uint32_t seq);           /* uid string */
+uint64_t    cfb_index_seq_taxid(const cfb_index*, uint32_t seq);
+/* returns 1 if taxid is a tree node; rank = TaxonomyNode.rank (taxonomy.h:16), leaf flag */
+int         cfb_index_tax_node(const cfb_index*, uint64_t taxid, uint64_t* parent, int* rank, int* leaf);
+
+/* Replaces: Classifier ctor arguments (classifier.h:135-143) + ReportingParams (aln_sink.h:573). */
+typedef struct {
+	int32_t khits;            /* -k, default 5 */
+	int32_t min_hitlen;       /* --min-hitlen, default 22, clamped to >= 15 (centrifuge.cpp:1401) */
+	int32_t tree_traverse;    /* 0 for --no-traverse */
+	int32_t class_rank_slot;  /* rank_to_pathID(--classification-rank): 0 strain .. 9 domain; 255 = none */
+	const uint64_t* host_taxids;     uint64_t n_host_taxids;      /* --host-taxids as given */
+	const uint64_t* excluded_taxids; uint64_t n_excluded_taxids;  /* --exclude-taxids as given */
+} cfb_params;
+void cfb_params_default(cfb_params*);
+
+/* One context = one CUDA stream set + staging buffers, bound to the index's device.
+ * max_units / max_bases size the device buffers (they grow on demand). */
+int  cfb_ctx_create(const cfb_index*, const cfb_params*, cfb_ctx** out);
+void cfb_ctx_destroy(cfb_ctx*);
+
+/* A batch of units.  Unit i is read i (n_mates==1) or pair i (n_mates==2).
+ * bases: 1 byte per base, 0..3 = ACGT, 4 = N (BTDnaString encoding, sstring.h), forward
+ * strand as parsed.  mate m of unit i lives at bases[off[m][i] .. off[m][i]+len[m][i]).
+ * flags[i]: bit0 = mate 1 passes the caller's filters (N/len/qc, centrifuge.cpp:2550-2596),
+ * bit1 = mate 2 passes.  A unit with no passing mate yields zero records ("unclassified").
+ * All arrays are caller-owned host memory (pinned memory from cfb_host_alloc is fastest). */
+typedef struct {
+	uint64_t n_units;
+	int32_t  n_mates;            /* 1 or 2 */
+	const uint8_t*  bases;  uint64_t n_bases;
+	const uint64_t* off[2];
+	const uint32_t* len[2];
+	const uint8_t*  flags;       /* NULL = all mates pass */
+} cfb_batch;
+
+/* One AlnRes worth of data (aligner_result.h:321): what Classifier::go hands sink.report(). */
+typedef struct {
+	uint64_t taxid;
+	uint32_t score;
+	uint32_t hitlen;    /* (uint64_t)summedHitLen */
+	uint32_t uid;       /* sequence index, CFB_UID_NONE after tree traversal merged it */
+	uint32_t pad;
+} cfb_rec;
+
+/* Library-owned result of one batch; valid until the next submit on the same slot.
+ * Records of unit i are recs[rec_off[i] .. rec_off[i+1]), in Classifier::_hitMap order.
+ * rec_off[i]==rec_off[i+1] means the reference would have called reportUnclassified(). */
+typedef struct {
+	uint64_t n_units;
+	uint64_t n_recs;
+	const uint32_t* rec_off;   /* n_units+1 entries */
+	const cfb_rec*  recs;
+} cfb_result;
+
+/* Synchronous: H2D, kernels, D2H, returns when the result is in host memory. */
+int cfb_classify_batch(cfb_ctx*, const cfb_batch*, cfb_result* out);
+
+/* Pipelined: up to cfb_ctx_slots() batches in flight on independent streams.
+ * submit copies the caller's arrays into pinned staging before returning. */
+int cfb_ctx_slots(const cfb_ctx*);
+int cfb_classify_submit(cfb_ctx*, int slot, const cfb_batch*);
+int cfb_classify_wait(cfb_ctx*, int slot, cfb_result* out);
+
+/* Device-resident variant used by the roofline measurement: inputs already in HBM
+ * (uploaded once by cfb_batch_upload), only kernels run.  kernel_ms (optional, 5 floats)
+ * receives CUDA-event times of {search, prep+rows, resolve, score+compact, total}. */
+typedef struct cfb_dbatch cfb_dbatch;
+int  cfb_batch_upload(cfb_ctx*, const cfb_batch*, cfb_dbatch** out);
+void cfb_dbatch_free(cfb_ctx*, cfb_dbatch*);
+int  cfb_classify_resident(cfb_ctx*, cfb_dbatch*, float* kernel_ms, uint64_t* n_recs);
+/* copy the last resident result to host (for parity checks) */
+int  cfb_resident_result(cfb_ctx*, cfb_result* out);
+
+/* Operation counters of the last batch on this ctx (same definition as SURVEY.md 8d):
+ * {units, partial_searches, ftab_probes, sides_search, walk_steps, rows_resolved, lf_steps_total, ext_searches} */
+int cfb_ctx_counters(cfb_ctx*, uint64_t out[8]);
+int cfb_ctx_kernel_launches(const cfb_ctx*, uint64_t* n);
+
+void* cfb_host_alloc(size_t bytes);   /* pinned host memory */
+void  cfb_host_free(void*);
+
+/* Device unit-test hooks (tests/ only): run the cooperative LF / resolve primitives on
+ * arrays of rows.  out[i] = LF(rows[i], chars[i]) ; chars[i] > 3 means BWT[rows[i]]. */
+int cfb_test_lf(const cfb_index*, const uint64_t* rows, const uint8_t* chars, uint64_t n, uint64_t* out);
+int cfb_test_resolve(const cfb_index*, const uint64_t* rows, uint64_t n, uint32_t* out);
+
+const char* cfb_last_error(void);
+const char* cfb_version(void);
+
+/* ---- host driver (libcfb200_host): drop-in for `centrifuge-class` ------------------
+ * Replaces: extern "C" int centrifuge(int argc, const char** argv) (centrifuge.cpp:3345).
+ * Same argv conventions and exit codes for the options it implements; unknown options
+ * are rejected with exit code 1 like the reference's getopt table does. */
+int cfb_run(int argc, const char** argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFB200_H_ */
