@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py -- reads/s of the classification hot path on B200 (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic 100 bp single-end reads against a
+synthetic genus/species index (SURVEY.md Appendix C recipe) replicated in each GPU's HBM.
+
+  value     reads/s with the batch already resident in HBM (kernels only, CUDA events, max over ranks)
+  e2e       reads/s through cfb_classify_submit/wait with HOST buffers: H2D of the packed reads and
+            D2H of the result records inside the timed region
+  roofline  k_search: algorithmic bytes (128 B per side touched + 16 B per ftab probe, counted by the
+            kernel's own counters in a separate un-timed pass) / its CUDA-event time, vs measured HBM peak
+  cpu_baseline   the unmodified reference binary (oracle/_ref/centrifuge-class -p <cores>) on a bounded sample
+
+`--impl reference` times that reference binary instead (all host threads, bounded sample per step).
+Multi-GPU: one process per GPU (torchrun), reads sharded, index replicated, one NCCL all-reduce of the
+dense per-taxon count vector at the end of every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+REF_CLASS = os.path.join(ROOT, "oracle", "_ref", "centrifuge-class")
+REF_BUILD = os.path.join(ROOT, "oracle", "_ref", "centrifuge-build-bin")
+CACHE = os.environ.get("CFB_BENCH_CACHE", "/tmp/cfb200_bench")
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------ workload
+def workload_genomes(genera, species, length, seed):
+    import synth
+    return synth.make_genomes(genera, species, length, seed)
+
+
+def get_index(genera, species, length, seed):
+    """Synthetic index on local disk (built once per box)."""
+    tag = "g%d_s%d_l%d_seed%d" % (genera, species, length, seed)
+    d = os.path.join(CACHE, tag)
+    base = os.path.join(d, "idx")
+    if os.path.exists(base + ".4.cf") and os.path.exists(os.path.join(d, "done")):
+        return base, d
+    os.makedirs(d, exist_ok=True)
+    import synth
+    t0 = time.time()
+    synth.write_genomes(d, genera, species, length, seed)
+    ncpu = os.cpu_count() or 8
+    with open(os.path.join(d, "build.log"), "w") as lg:
+        subprocess.check_call([REF_BUILD, "-p", str(min(ncpu, 64)), "--conversion-table", os.path.join(d, "conv.tsv"),
+                               "--taxonomy-tree", os.path.join(d, "nodes.dmp"), "--name-table", os.path.join(d, "names.dmp"),
+                               os.path.join(d, "genomes.fa"), base], stdout=lg, stderr=lg)
+    open(os.path.join(d, "done"), "w").close()
+    log("index %s built in %.1f s" % (tag, time.time() - t0))
+    return base, d
+
+
+def make_reads(seqs, n, rdlen, seed):
+    """Vectorised sampler: uniform genome/position/strand, 1% substitutions, 0.1% N, 5% random reads.
+    Returns codes (n, rdlen) uint8 in 0..4."""
+    rng = np.random.default_rng(seed)
+    G = np.stack(seqs)
+    L = G.shape[1]
+    si = rng.integers(0, G.shape[0], n)
+    pos = rng.integers(0, L - rdlen, n)
+    R = G[si[:, None], pos[:, None] + np.arange(rdlen)[None, :]]
+    sub = rng.random((n, rdlen)) < 0.01
+    R = np.where(sub, (R + 1) & 3, R).astype(np.uint8)
+    rc = rng.random(n) < 0.5
+    R[rc] = (3 - R[rc])[:, ::-1]
+    rnd = rng.random(n) < 0.05
+    R[rnd] = rng.integers(0, 4, size=(int(rnd.sum()), rdlen), dtype=np.uint8)
+    R[rng.random((n, rdlen)) < 0.001] = 4
+    return np.ascontiguousarray(R)
+
+
+def write_fastq(path, codes, prefix="r"):
+    asc = np.frombuffer(b"ACGTN", dtype=np.uint8)[codes]
+    n, L = asc.shape
+    q = b"I" * L
+    with open(path, "wb") as f:
+        for i in range(n):
+            f.write(b"@%s%d\n" % (prefix.encode(), i) + asc[i].tobytes() + b"\n+\n" + q + b"\n")
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.samples, self.reasons, self.stop_flag, self.maxmhz = dev, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.maxmhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons)}
+
+
+def ref_reads_per_s(base, fq, threads):
+    t0 = time.time()
+    subprocess.check_call([REF_CLASS, "-q", "-x", base, "-U", fq, "-p", str(threads), "-S", "/dev/null", "--report-file", "/dev/null"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return time.time() - t0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cfb200", choices=["cfb200", "reference"])
+    ap.add_argument("--genera", type=int, default=int(os.environ.get("CFB_BENCH_GENERA", 10)))
+    ap.add_argument("--species", type=int, default=int(os.environ.get("CFB_BENCH_SPECIES", 10)))
+    ap.add_argument("--genome-len", type=int, default=int(os.environ.get("CFB_BENCH_GENOME_LEN", 1000000)))
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("CFB_BENCH_READS", 2000000)), help="reads per step per GPU")
+    ap.add_argument("--rdlen", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("CFB_BENCH_CPU_SAMPLE", 400000)))
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    ncores = os.cpu_count() or 1
+    workload = "synthetic %d genera x %d species x %d bp index (%.0f Mbp), %d x %d bp SE reads per step per GPU" % (
+        a.genera, a.species, a.genome_len, a.genera * a.species * a.genome_len / 1e6, a.reads, a.rdlen)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        base, d = get_index(a.genera, a.species, a.genome_len, 12345)
+        seqs = workload_genomes(a.genera, a.species, a.genome_len, 12345)
+        n = a.cpu_sample
+        fq = os.path.join(d, "sample_%d.fq" % n)
+        if not os.path.exists(fq):
+            write_fastq(fq, make_reads(seqs, n, a.rdlen, 999))
+        for _ in range(min(a.warmup, 1)):
+            ref_reads_per_s(base, fq, ncores)
+        t = [ref_reads_per_s(base, fq, ncores) for _ in range(a.steps)]
+        tot = sum(t)
+        val = n * a.steps / tot
+        print(json.dumps({"metric": "reads/sec (100 bp SE classification)", "value": val, "unit": "reads/s", "n_gpus": a.gpus, "steps": a.steps,
+                          "warmup": min(a.warmup, 1), "ms_per_step": 1000 * tot / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "u64", "data": "synthetic", "impl": "reference",
+                          "config": {"workload": workload, "sample": "%d reads per step (bounded sample of the workload), FASTQ in, TSV to /dev/null, index load included" % n},
+                          "cpu_baseline": {"value": val, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "%d reads x %d steps, centrifuge-class -p %d" % (n, a.steps, ncores)},
+                          "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    from centrifuge_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the cfb200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        base, d = get_index(a.genera, a.species, a.genome_len, 12345)
+    if dist:
+        dist.barrier()
+    base, d = get_index(a.genera, a.species, a.genome_len, 12345)
+    seqs = workload_genomes(a.genera, a.species, a.genome_len, 12345)
+    codes = make_reads(seqs, a.reads, a.rdlen, 1000 + rank)
+    n = a.reads
+    bases = codes.reshape(-1)
+    lens = np.full(n, a.rdlen, dtype=np.uint32)
+    offs = np.arange(n, dtype=np.uint64) * np.uint64(a.rdlen)
+    flags = ((codes == 4).sum(axis=1) <= int(0.15 * a.rdlen)).astype(np.uint8)
+    batch = capi.make_batch(bases, offs, lens, None, None, flags)
+
+    t0 = time.time()
+    ix = capi.Index(base, local)
+    log("rank %d: index in HBM: %.2f GB in %.1f s (%d sides)" % (rank, ix.info.device_bytes / 1e9, time.time() - t0, ix.info.num_sides))
+    ctx = capi.Context(ix)
+    n_tax = int(ix.info.n_tax_nodes) + 1
+    counts = torch.zeros(n_tax * 2, dtype=torch.int64, device="cuda")
+
+    def fold_counts(off, recs):
+        # dense per-taxon {numReads, numUniqueReads}: one vector per rank, summed by NCCL
+        return None
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- un-timed counter pass (algorithmic bytes of this exact batch)
+    os.environ["CFB_COUNT"] = "1"
+    cctx = capi.Context(ix)
+    del os.environ["CFB_COUNT"]
+    cctx.classify(batch)
+    ctr = cctx.counters()
+    cctx.close()
+    sample_w = ix.info.sample_bytes
+    bytes_search = 128 * ctr["sides_search"] + 16 * ctr["ftab_probes"]
+    bytes_walk = 128 * ctr["walk_steps"] + sample_w * ctr["rows_resolved"]
+
+    # ---------------- value: resident batch, kernels only
+    dbatch = ctx.upload(batch)
+    for _ in range(a.warmup):
+        ctx.classify_resident(dbatch)
+    sampler = ClockSampler(local); sampler.start()
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    kms = np.zeros(5)
+    for _ in range(a.steps):
+        ms, nrec = ctx.classify_resident(dbatch)       # per-stage CUDA-event times on the kernels' own stream
+        kms += np.array(ms)
+        if dist:
+            dist.all_reduce(counts)
+    sync_all()
+    wall = time.perf_counter() - t_wall0
+    launches_value = ctx.launches()
+    # device time of the timed region = sum of the per-step event spans (each step is synchronised)
+    step_ms = kms[4] / a.steps
+    t_dev = torch.tensor([kms[4] / 1000.0, wall], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    dev_s, wall_s = float(t_dev[0]), float(t_dev[1])
+    value = world * n * a.steps / dev_s
+
+    # ---------------- e2e: host buffers in, host records out, 2 batches in flight
+    nslots = ctx.n_slots
+    for _ in range(min(a.warmup, 2)):
+        ctx.submit(0, batch); ctx.wait(0, copy=False)
+    sync_all()
+    t0 = time.perf_counter()
+    inflight = []
+    d2h = 0
+    for s in range(a.steps):
+        slot = s % nslots
+        if len(inflight) == nslots:
+            _, nr = ctx.wait(inflight.pop(0), copy=False); d2h += nr * 24 + (n + 1) * 4
+        ctx.submit(slot, batch); inflight.append(slot)
+    while inflight:
+        _, nr = ctx.wait(inflight.pop(0), copy=False); d2h += nr * 24 + (n + 1) * 4
+    if dist:
+        dist.all_reduce(counts)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = world * n * a.steps / float(te[0])
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    launches_total = ctx.launches()
+    h2d = bases.nbytes + offs.nbytes + lens.nbytes + flags.nbytes
+
+    peak, peak_src = measured_peak()
+    search_s = kms[0] / 1000.0 / a.steps
+    achieved = bytes_search / search_s / 1e9
+    out = {
+        "metric": "reads/sec (100 bp SE classification)", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1000 * dev_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload, "index_bytes_hbm": int(ix.info.device_bytes), "l2": "index replica %.0f MB vs 126 MB L2; same batch re-walked every step" % (ix.info.device_bytes / 1e6),
+                   "parallelism": "reads sharded over %d GPU(s), index replicated, 1 NCCL all-reduce of per-taxon counts per step" % world},
+        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h // max(a.steps, 1))},
+        "gpu_launches": int(launches_value),
+        "roofline": {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_search), "kernel_ms": 1000 * search_s,
+                     "sides_per_read": ctr["sides_search"] / max(ctr["units"], 1), "walk_bytes_per_launch": int(bytes_walk)},
+        "kernel_ms": {"search": kms[0] / a.steps, "prep_rows": kms[1] / a.steps, "resolve": kms[2] / a.steps, "score_compact": kms[3] / a.steps, "total": step_ms},
+        "clocks": sampler.summary(),
+        "wall_s_value_region": wall_s,
+    }
+    if rank == 0:
+        # bounded CPU baseline: the unmodified reference binary on the host cores
+        try:
+            ns = a.cpu_sample
+            fq = os.path.join(d, "sample_%d.fq" % ns)
+            if not os.path.exists(fq):
+                write_fastq(fq, make_reads(seqs, ns, a.rdlen, 999))
+            tt = ref_reads_per_s(base, fq, ncores)
+            out["cpu_baseline"] = {"value": ns / tt, "unit": "reads/s", "cores": ncores, "kind": "reference",
+                                   "sample": "%d reads, centrifuge-class -p %d, FASTQ in, TSV to /dev/null, index load included (%.1f s)" % (ns, ncores, tt)}
+        except Exception as e:  # noqa: BLE001
+            out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "failed: %s" % e}
+        print(json.dumps(out))
+    ctx.close(); ix.close()
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,201 @@
+"""ctypes binding of include/cfb200.h (the C ABI of libcfb200.so).
+
+Python is plumbing only: every call below lands in the CUDA library.  There is no CPU
+fallback -- loading the library or creating a context without a usable sm_100 device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcfb200.so")
+
+CFB_UID_NONE = 0xFFFFFFFF
+REC_DTYPE = np.dtype([("taxid", "<u8"), ("score", "<u4"), ("hitlen", "<u4"), ("uid", "<u4"), ("pad", "<u4")])
+
+_lib = None
+
+
+class CfbError(RuntimeError):
+    pass
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [("len", C.c_uint64), ("num_sides", C.c_uint64), ("n_seqs", C.c_uint64), ("n_tax_nodes", C.c_uint64),
+                ("n_boundaries", C.c_uint64), ("line_rate", C.c_int32), ("off_rate", C.c_int32), ("ftab_chars", C.c_int32),
+                ("sample_bytes", C.c_int32), ("compressed", C.c_int32), ("device", C.c_int32), ("device_bytes", C.c_uint64)]
+
+
+class Params(C.Structure):
+    _fields_ = [("khits", C.c_int32), ("min_hitlen", C.c_int32), ("tree_traverse", C.c_int32), ("class_rank_slot", C.c_int32),
+                ("host_taxids", C.POINTER(C.c_uint64)), ("n_host_taxids", C.c_uint64),
+                ("excluded_taxids", C.POINTER(C.c_uint64)), ("n_excluded_taxids", C.c_uint64)]
+
+
+class BatchC(C.Structure):
+    _fields_ = [("n_units", C.c_uint64), ("n_mates", C.c_int32), ("bases", C.POINTER(C.c_uint8)), ("n_bases", C.c_uint64),
+                ("off", C.POINTER(C.c_uint64) * 2), ("len", C.POINTER(C.c_uint32) * 2), ("flags", C.POINTER(C.c_uint8))]
+
+
+class ResultC(C.Structure):
+    _fields_ = [("n_units", C.c_uint64), ("n_recs", C.c_uint64), ("rec_off", C.POINTER(C.c_uint32)), ("recs", C.c_void_p)]
+
+
+def lib():
+    """Load libcfb200.so (building nothing: run centrifuge_b200.build first)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CfbError("libcfb200.so is not built (python -m centrifuge_b200.build); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.cfb_last_error.restype = C.c_char_p
+        L.cfb_version.restype = C.c_char_p
+        L.cfb_index_seq_name.restype = C.c_char_p
+        L.cfb_index_seq_taxid.restype = C.c_uint64
+        L.cfb_host_alloc.restype = C.c_void_p
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise CfbError("cfb200 error %d: %s" % (rc, lib().cfb_last_error().decode()))
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Index:
+    def __init__(self, basename, device=0):
+        self.h = C.c_void_p()
+        _ck(lib().cfb_index_load(basename.encode(), C.c_int(device), C.byref(self.h)))
+        self.info = IndexInfo()
+        _ck(lib().cfb_index_get_info(self.h, C.byref(self.info)))
+
+    def seq_name(self, i):
+        s = lib().cfb_index_seq_name(self.h, C.c_uint32(i))
+        return s.decode() if s is not None else None
+
+    def seq_taxid(self, i):
+        return int(lib().cfb_index_seq_taxid(self.h, C.c_uint32(i)))
+
+    def tax_node(self, taxid):
+        par, rank, leaf = C.c_uint64(), C.c_int(), C.c_int()
+        ok = lib().cfb_index_tax_node(self.h, C.c_uint64(taxid), C.byref(par), C.byref(rank), C.byref(leaf))
+        return (int(par.value), rank.value, leaf.value) if ok else None
+
+    def close(self):
+        if self.h:
+            lib().cfb_index_free(self.h)
+            self.h = C.c_void_p()
+
+
+def make_params(k=5, min_hitlen=22, traverse=True, rank_slot=0, host=(), excl=()):
+    p = Params()
+    lib().cfb_params_default(C.byref(p))
+    p.khits, p.min_hitlen, p.tree_traverse, p.class_rank_slot = k, min_hitlen, 1 if traverse else 0, rank_slot
+    p._h = (C.c_uint64 * max(1, len(host)))(*host)
+    p._e = (C.c_uint64 * max(1, len(excl)))(*excl)
+    p.host_taxids, p.n_host_taxids = C.cast(p._h, C.POINTER(C.c_uint64)), len(host)
+    p.excluded_taxids, p.n_excluded_taxids = C.cast(p._e, C.POINTER(C.c_uint64)), len(excl)
+    return p
+
+
+def make_batch(bases, off1, len1, off2=None, len2=None, flags=None):
+    """numpy arrays -> BatchC (keeps references alive on the returned object)."""
+    b = BatchC()
+    b.n_units = len(len1)
+    b.n_mates = 2 if off2 is not None else 1
+    b.bases, b.n_bases = _p(bases, C.c_uint8), bases.size
+    b.off[0], b.len[0] = _p(off1, C.c_uint64), _p(len1, C.c_uint32)
+    if off2 is not None:
+        b.off[1], b.len[1] = _p(off2, C.c_uint64), _p(len2, C.c_uint32)
+    if flags is not None:
+        b.flags = _p(flags, C.c_uint8)
+    b._keep = (bases, off1, len1, off2, len2, flags)
+    return b
+
+
+def _result(res):
+    n = int(res.n_units)
+    nrec = int(res.n_recs)
+    if n == 0:
+        return np.zeros(1, dtype=np.uint32), np.zeros(0, dtype=REC_DTYPE)
+    off = np.ctypeslib.as_array(res.rec_off, shape=(n + 1,)).copy()
+    if nrec:
+        buf = (C.c_char * (nrec * REC_DTYPE.itemsize)).from_address(res.recs)
+        recs = np.frombuffer(buf, dtype=REC_DTYPE).copy()
+    else:
+        recs = np.zeros(0, dtype=REC_DTYPE)
+    return off, recs
+
+
+class Context:
+    def __init__(self, index, params=None):
+        self.index = index
+        self.params = params if params is not None else make_params()
+        self.h = C.c_void_p()
+        _ck(lib().cfb_ctx_create(index.h, C.byref(self.params), C.byref(self.h)))
+        self.n_slots = lib().cfb_ctx_slots(self.h)
+
+    def classify(self, batch):
+        res = ResultC()
+        _ck(lib().cfb_classify_batch(self.h, C.byref(batch), C.byref(res)))
+        return _result(res)
+
+    def submit(self, slot, batch):
+        _ck(lib().cfb_classify_submit(self.h, C.c_int(slot), C.byref(batch)))
+
+    def wait(self, slot, copy=True):
+        res = ResultC()
+        _ck(lib().cfb_classify_wait(self.h, C.c_int(slot), C.byref(res)))
+        return _result(res) if copy else (int(res.n_units), int(res.n_recs))
+
+    def upload(self, batch):
+        d = C.c_void_p()
+        _ck(lib().cfb_batch_upload(self.h, C.byref(batch), C.byref(d)))
+        return d
+
+    def classify_resident(self, dbatch):
+        ms = (C.c_float * 5)()
+        nrec = C.c_uint64()
+        _ck(lib().cfb_classify_resident(self.h, dbatch, ms, C.byref(nrec)))
+        return list(ms), int(nrec.value)
+
+    def resident_result(self):
+        res = ResultC()
+        _ck(lib().cfb_resident_result(self.h, C.byref(res)))
+        return _result(res)
+
+    def counters(self):
+        out = (C.c_uint64 * 8)()
+        _ck(lib().cfb_ctx_counters(self.h, out))
+        names = ["units", "partial_searches", "ftab_probes", "sides_search", "walk_steps", "rows_resolved", "lf_steps", "ext_searches"]
+        return dict(zip(names, [int(x) for x in out]))
+
+    def launches(self):
+        n = C.c_uint64()
+        _ck(lib().cfb_ctx_kernel_launches(self.h, C.byref(n)))
+        return int(n.value)
+
+    def close(self):
+        if self.h:
+            lib().cfb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def test_lf(index, rows, chars):
+    rows = np.ascontiguousarray(rows, dtype=np.uint64)
+    chars = np.ascontiguousarray(chars, dtype=np.uint8)
+    out = np.zeros(len(rows), dtype=np.uint64)
+    _ck(lib().cfb_test_lf(index.h, _p(rows, C.c_uint64), _p(chars, C.c_uint8), C.c_uint64(len(rows)), _p(out, C.c_uint64)))
+    return out
+
+
+def test_resolve(index, rows):
+    rows = np.ascontiguousarray(rows, dtype=np.uint64)
+    out = np.zeros(len(rows), dtype=np.uint32)
+    _ck(lib().cfb_test_resolve(index.h, _p(rows, C.c_uint64), C.c_uint64(len(rows)), _p(out, C.c_uint32)))
+    return out

@@ -1,0 +1,603 @@
+// cf_host.cpp -- host worker around the C ABI: the part of `centrifuge-class` that stays on the CPU.
+//
+// Replaces (paths relative to the reference tree):
+//   option handling of the classification-relevant flags          centrifuge.cpp:530-695,1495
+//   PatternSource FASTA/FASTQ parsing + per-read seed              pat.cpp:725-1157, pat.h:55-91
+//   per-read filters (N ceiling 0.15*len, length >= 2)             centrifuge.cpp:2550-2596, scoring.cpp:104-168
+//   AlnSinkWrap::finishRead -> selectByScore -> TSV row            aln_sink.h:1634-1927,2202-2361
+//   SpeciesMetrics + SQUAREM abundance + report TSV                aln_sink.h:56-495, centrifuge.cpp:3231-3319
+// The classification itself (Classifier::go) happens on the GPU through cfb_classify_submit/wait;
+// reads are cut into batches, two batches are in flight, and output order is input order
+// (what the reference produces with -p 1 or --reorder).
+#include "../../include/cfb200.h"
+#include "cf_index.h"
+
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace cfb;
+
+// the loader's HostIndex lives inside cfb_index; the driver only needs these accessors
+extern "C" const cfb::HostIndex* cfb_index_host(const cfb_index*);
+
+namespace {
+
+struct Options {
+	std::string index, out = "-", report = "centrifuge_report.tsv";
+	std::vector<std::string> singles, mates1, mates2;
+	bool fasta = false, abundance = true, quiet = false, time = false;
+	int device = 0;
+	uint64_t skip = 0, upto = std::numeric_limits<uint64_t>::max();
+	uint32_t seed = 0;
+	size_t batch_units = 1u << 18;
+	cfb_params prm; std::vector<uint64_t> host, excl;
+	int trim5 = 0, trim3 = 0;
+};
+
+struct OptDesc { const char* name; int has_arg; };
+static const OptDesc kLong[] = {
+	{"quiet", 0}, {"time", 0}, {"seed", 1}, {"upto", 1}, {"qupto", 1}, {"skip", 1}, {"version", 0}, {"help", 0}, {"threads", 1},
+	{"reorder", 0}, {"mm", 0}, {"wrapper", 1}, {"arg-desc", 0}, {"report-file", 1}, {"no-abundance", 0}, {"no-traverse", 0},
+	{"min-hitlen", 1}, {"host-taxids", 1}, {"exclude-taxids", 1}, {"classification-rank", 1}, {"trim5", 1}, {"trim3", 1},
+	{"device", 1}, {"batch-units", 1}, {NULL, 0}};
+static const char* kShort = "fqtu:s:p:k:1:2:U:x:S:3:5:h";
+
+std::vector<std::string> split(const std::string& s, char d) {
+	std::vector<std::string> v; std::string t; std::stringstream ss(s);
+	while(std::getline(ss, t, d)) if(!t.empty()) v.push_back(t);
+	return v;
+}
+
+// ------------------------------------------------------------------------------ reads
+struct FileIn {       // buffered byte source with one-byte peek
+	FILE* f = NULL; std::vector<unsigned char> buf; size_t pos = 0, end = 0;
+	bool open(const std::string& p) { f = p == "-" ? stdin : fopen(p.c_str(), "rb"); buf.resize(1 << 22); return f != NULL; }
+	void close() { if(f && f != stdin) fclose(f); f = NULL; }
+	inline bool fill() { if(!f) return false; end = fread(buf.data(), 1, buf.size(), f); pos = 0; return end > 0; }
+	inline int get() { if(pos == end && !fill()) return -1; return buf[pos++]; }
+	inline int peek() { if(pos == end && !fill()) return -1; return buf[pos]; }
+};
+
+static uint8_t g_asc2dna[256];
+static uint8_t g_dnacat[256];
+static void init_tables() {
+	static bool done = false; if(done) return; done = true;
+	memset(g_asc2dna, 0, 256); memset(g_dnacat, 0, 256);
+	g_asc2dna['C'] = g_asc2dna['c'] = 1; g_asc2dna['G'] = g_asc2dna['g'] = 2; g_asc2dna['T'] = g_asc2dna['t'] = 3; g_asc2dna['N'] = g_asc2dna['n'] = 4;
+	const char* k = "ABCDGHKMNRSTVWXY";                  // asc2dnacat > 0 (alphabet.cpp:36-58) plus '-'
+	for(const char* p = k; *p; p++) { g_dnacat[(int)*p] = 1; g_dnacat[tolower(*p)] = 1; }
+	g_dnacat['-'] = 1;
+}
+
+struct Rec {          // one parsed read
+	std::string name; std::vector<uint8_t> seq; uint32_t qx = 0;   // qx = quality contribution to the seed
+	bool ok = false;
+};
+
+// FASTA record, pat.cpp:725-849.  Returns false at end of input.
+static bool parse_fasta(FileIn& in, Rec& r, uint64_t& count, bool& first, int trim5, int trim3) {
+	r.name.clear(); r.seq.clear(); r.qx = 0;
+	int c = in.get();
+	if(c < 0) return false;
+	while(c == '#' || c == ';' || c == '\r' || c == '\n') {
+		if(c == '#' || c == ';') { for(;;) { int d = in.peek(); if(d < 0 || d == '\n' || d == '\r') break; in.get(); } }
+		c = in.get();
+		if(c < 0) return false;
+	}
+	if(first) { if(c != '>') { std::cerr << "Error: reads file does not look like a FASTA file" << std::endl; throw 1; } first = false; }
+	c = in.get();
+	for(;;) {
+		if(c < 0) return false;
+		if(c == '\n' || c == '\r') {
+			while(c == '\n' || c == '\r') { if(in.peek() == '>') break; c = in.get(); if(c < 0) return false; }
+			break;
+		}
+		r.name.push_back((char)c);
+		if(in.peek() == '>') break;
+		c = in.get();
+	}
+	int begin = 0;
+	if(!((c == '\n' || c == '\r') && in.peek() == '>')) {
+		while(c != '>' && c >= 0) {
+			if(g_dnacat[c] && begin++ >= trim5) r.seq.push_back(g_asc2dna[c]);
+			if(in.peek() == '>') break;
+			c = in.get();
+		}
+	}
+	if(trim3 > 0) r.seq.resize(r.seq.size() > (size_t)trim3 ? r.seq.size() - trim3 : 0);
+	// quality of every FASTA base is 'I' (pat.cpp:828): fold into the seed contribution
+	for(size_t i = 0; i < r.seq.size(); i++) r.qx ^= ((uint32_t)'I' << ((i & 3) << 3));
+	if(r.name.empty()) { char b[32]; snprintf(b, sizeof b, "%llu", (unsigned long long)count); r.name = b; }
+	count++;
+	return true;
+}
+
+// FASTQ record, pat.cpp:852-1157 (phred33, no colour/fuzzy/int-quals modes).
+static bool parse_fastq(FileIn& in, Rec& r, uint64_t& count, bool& first, int trim5, int trim3) {
+	r.name.clear(); r.seq.clear(); r.qx = 0;
+	int c;
+	if(first) {
+		c = in.get();
+		while(c == '\n' || c == '\r') c = in.get();
+		if(c < 0) return false;
+		if(c != '@') { std::cerr << "Error: reads file does not look like a FASTQ file" << std::endl; throw 1; }
+		first = false;
+	}
+	for(;;) {
+		c = in.get();
+		if(c < 0) return false;
+		if(c == '\n' || c == '\r') { while(c == '\n' || c == '\r') { c = in.get(); if(c < 0) return false; } break; }
+		r.name.push_back((char)c);
+	}
+	int nread = 0;
+	while(c != '+') {
+		if(c == '.') c = 'N';
+		if(isalpha(c)) { if(nread >= trim5) r.seq.push_back(g_asc2dna[c]); nread++; }
+		c = in.get();
+		if(c < 0) return false;
+	}
+	if(trim3 > 0) r.seq.resize(r.seq.size() > (size_t)trim3 ? r.seq.size() - trim3 : 0);
+	for(;;) { int d = in.get(); if(d < 0) break; if(d == '\n' || d == '\r') { while(in.peek() == '\n' || in.peek() == '\r') in.get(); break; } }
+	if(nread == 0) { if(in.peek() == '@') in.get(); count++; return true; }
+	size_t qn = 0; int qi = 0;
+	for(;;) {
+		c = in.get();
+		if(c < 0 || c == '\r' || c == '\n') break;
+		if(qi >= trim5 && qn < r.seq.size()) { r.qx ^= ((uint32_t)(c & 0xff) << ((qn & 3) << 3)); qn++; }
+		qi++;
+	}
+	if(qn < r.seq.size()) { std::cerr << "Error: Read " << r.name << " has more read characters than quality values." << std::endl; throw 1; }
+	while(in.peek() == '\n' || in.peek() == '\r') in.get();
+	in.get();                                              // '@' of the next record (or EOF)
+	if(r.name.empty()) { char b[32]; snprintf(b, sizeof b, "%llu", (unsigned long long)count); r.name = b; }
+	count++;
+	return true;
+}
+
+static uint32_t read_seed(const Rec& r, uint32_t seed) {   // genRandSeed pat.h:55-91
+	uint32_t rseed = (seed + 101) * 59 * 61 * 67 * 71 * 73 * 79 * 83;
+	const size_t n = r.seq.size();
+	for(size_t i = 0; i < n; i++) rseed ^= ((uint32_t)r.seq[i] << ((i & 15) << 1));
+	rseed ^= r.qx;
+	for(size_t i = 0; i < r.name.size(); i++) { const int p = (int)r.name[i]; if(p == '/') break; rseed ^= ((uint32_t)p << ((i & 3) << 3)); }
+	return rseed;
+}
+static bool passes_filters(const std::vector<uint8_t>& s) {   // nFilter (NCEIL=L,0,0.15) + lenfilt
+	if(s.size() < 2) return false;
+	const size_t maxns = (size_t)(0.15 * (double)s.size());
+	size_t ns = 0;
+	for(size_t i = 0; i < s.size(); i++) if(s[i] == 4 && ++ns > maxns) return false;
+	return true;
+}
+
+struct HostBatch {     // one batch staged for the GPU plus what the formatter needs afterwards
+	std::vector<uint8_t> bases; std::vector<uint64_t> off[2]; std::vector<uint32_t> len[2]; std::vector<uint8_t> flags;
+	std::vector<uint32_t> seedA, seedB; std::vector<char> names; std::vector<uint32_t> name_off;
+	bool paired = false; size_t n = 0;
+	void clear(bool p) { bases.clear(); for(int m = 0; m < 2; m++) { off[m].clear(); len[m].clear(); } flags.clear(); seedA.clear(); seedB.clear(); names.clear(); name_off.clear(); paired = p; n = 0; }
+	void add(const Rec& a, const Rec* b, uint32_t seed) {
+		off[0].push_back(bases.size()); len[0].push_back((uint32_t)a.seq.size()); bases.insert(bases.end(), a.seq.begin(), a.seq.end());
+		uint8_t fl = passes_filters(a.seq) ? 1 : 0;
+		seedA.push_back(read_seed(a, seed));
+		if(paired) {
+			off[1].push_back(bases.size()); len[1].push_back((uint32_t)b->seq.size()); bases.insert(bases.end(), b->seq.begin(), b->seq.end());
+			if(!b->seq.empty() && passes_filters(b->seq)) fl |= 2;
+			seedB.push_back(b->seq.empty() ? 0u : read_seed(*b, seed));
+		}
+		flags.push_back(fl);
+		name_off.push_back((uint32_t)names.size()); names.insert(names.end(), a.name.begin(), a.name.end());
+		n++;
+	}
+};
+
+// ------------------------------------------------------------------------------ metrics
+struct IdsLess {       // SpeciesMetrics::IDs::operator< aln_sink.h:63-71
+	bool operator()(const std::vector<uint64_t>& a, const std::vector<uint64_t>& b) const {
+		if(a.size() != b.size()) return a.size() < b.size();
+		for(size_t i = 0; i < a.size(); i++) if(a[i] != b[i]) return a[i] < b[i];
+		return false;
+	}
+};
+struct Counts { uint64_t n_reads = 0, n_unique = 0; };
+struct Species {
+	std::map<uint64_t, Counts> counts;
+	std::map<std::vector<uint64_t>, uint64_t, IdsLess> observed;
+	std::vector<uint64_t> cur;
+	std::map<uint64_t, double> abundance_len;
+	uint64_t last_tax = ~0ull; Counts* last = NULL;
+	inline void add(uint64_t taxid, int64_t score, int64_t max_score, uint32_t nresult) {   // addSpeciesCounts aln_sink.h:142-172
+		if(taxid != last_tax || !last) { last = &counts[taxid]; last_tax = taxid; }
+		last->n_reads++; if(nresult == 1) last->n_unique++;
+		if(score >= max_score) {
+			cur.push_back(taxid);
+			if(cur.size() == nresult) { std::sort(cur.begin(), cur.end()); observed[cur] += 1; cur.clear(); }
+		}
+	}
+};
+
+typedef std::map<std::vector<uint64_t>, uint64_t, IdsLess> Observed;
+
+static void em_step(const Observed& observed, const std::map<uint64_t, std::vector<uint64_t> >& anc, const std::map<uint64_t, uint64_t>& t2n,
+                    const std::vector<double>& p, std::vector<double>& pn, const std::vector<size_t>& len) {   // aln_sink.h:196-272
+	std::fill(pn.begin(), pn.end(), 0.0);
+	for(Observed::const_iterator it = observed.begin(); it != observed.end(); ++it) {
+		const std::vector<uint64_t>& ids = it->first; const uint64_t count = it->second;
+		double psum = 0.0;
+		for(size_t i = 0; i < ids.size(); i++) {
+			std::map<uint64_t, uint64_t>::const_iterator id = t2n.find(ids[i]);
+			if(id != t2n.end()) { psum += p[id->second]; continue; }
+			std::map<uint64_t, std::vector<uint64_t> >::const_iterator a = anc.find(ids[i]);
+			if(a == anc.end()) continue;
+			for(size_t c = 0; c < a->second.size(); c++) { std::map<uint64_t, uint64_t>::const_iterator ci = t2n.find(a->second[c]); if(ci != t2n.end()) psum += p[ci->second]; }
+		}
+		if(psum == 0.0) continue;
+		for(size_t i = 0; i < ids.size(); i++) {
+			std::map<uint64_t, uint64_t>::const_iterator id = t2n.find(ids[i]);
+			if(id != t2n.end()) { pn[id->second] += (count * (p[id->second] / psum)); continue; }
+			std::map<uint64_t, std::vector<uint64_t> >::const_iterator a = anc.find(ids[i]);
+			if(a == anc.end()) continue;
+			for(size_t c = 0; c < a->second.size(); c++) { std::map<uint64_t, uint64_t>::const_iterator ci = t2n.find(a->second[c]); if(ci != t2n.end()) pn[ci->second] += (count * (p[ci->second] / psum)); }
+		}
+	}
+	double sum = 0.0;
+	for(size_t i = 0; i < pn.size(); i++) sum += (pn[i] / len[i]);
+	for(size_t i = 0; i < pn.size(); i++) pn[i] = pn[i] / len[i] / sum;
+}
+
+static void calc_abundance(const HostIndex& h, Species& sp, size_t& iters, double& last_diff) {   // aln_sink.h:274-495
+	std::set<uint64_t> leaves;
+	for(Observed::const_iterator it = sp.observed.begin(); it != sp.observed.end(); ++it)
+		for(size_t i = 0; i < it->first.size(); i++) { const TaxNode* n = h.find_node(it->first[i]); if(n && n->leaf) leaves.insert(n->taxid); }
+	std::map<uint64_t, std::vector<uint64_t> > anc;
+	for(Observed::const_iterator it = sp.observed.begin(); it != sp.observed.end(); ++it)
+		for(size_t i = 0; i < it->first.size(); i++) {
+			const uint64_t tid = it->first[i];
+			if(leaves.count(tid) || anc.count(tid)) continue;
+			std::vector<uint64_t>& ch = anc[tid];
+			for(std::set<uint64_t>::const_iterator l = leaves.begin(); l != leaves.end(); ++l) {
+				for(uint64_t t = *l;;) {
+					const TaxNode* n = h.find_node(t);
+					if(!n) break;
+					if(tid == n->parent) ch.push_back(*l);
+					if(t == n->parent) break;
+					t = n->parent;
+				}
+			}
+			std::sort(ch.begin(), ch.end());
+		}
+	std::map<uint64_t, uint64_t> t2n; std::vector<double> p; std::vector<size_t> len;
+	for(Observed::const_iterator it = sp.observed.begin(); it != sp.observed.end(); ++it) {
+		const std::vector<uint64_t>& ids = it->first; const uint64_t count = it->second;
+		for(size_t i = 0; i < ids.size(); i++) {
+			const uint64_t tid = ids[i];
+			if(!leaves.count(tid)) continue;
+			std::map<uint64_t, uint64_t>::iterator f = t2n.find(tid);
+			if(f == t2n.end()) {
+				t2n[tid] = p.size(); p.push_back(1.0 / ids.size() * count);
+				std::map<uint64_t, uint64_t>::const_iterator s = h.sizes.find(tid);
+				len.push_back(s != h.sizes.end() ? (size_t)s->second : std::numeric_limits<size_t>::max());
+			} else p[f->second] += (1.0 / ids.size() * count);
+		}
+	}
+	{ double sum = 0.0; for(size_t i = 0; i < p.size(); i++) sum += (p[i] / len[i]); for(size_t i = 0; i < p.size(); i++) p[i] = (p[i] / len[i]) / sum; }
+	std::vector<double> pn(p.size()), pn2(p.size()), pr(p.size()), pv(p.size());
+	size_t it = 0; double diff = 0.0;
+	for(;;) {
+		em_step(sp.observed, anc, t2n, p, pn, len);
+		em_step(sp.observed, anc, t2n, pn, pn2, len);
+		double ssr = 0.0, ssv = 0.0;
+		for(size_t i = 0; i < p.size(); i++) { pr[i] = pn[i] - p[i]; ssr += pr[i] * pr[i]; pv[i] = pn2[i] - pn[i] - pr[i]; ssv += pv[i] * pv[i]; }
+		if(ssv > 0.0) {
+			const double g = -sqrt(ssr / ssv);
+			for(size_t i = 0; i < p.size(); i++) pn2[i] = std::max(0.0, p[i] - 2 * g * pr[i] + g * g * pv[i]);
+			em_step(sp.observed, anc, t2n, pn2, pn, len);
+		}
+		diff = 0.0;
+		for(size_t i = 0; i < p.size(); i++) diff += (p[i] > pn[i] ? p[i] - pn[i] : pn[i] - p[i]);
+		if(diff < 0.0000000001) break;
+		if(++it >= 10000) break;
+		p = pn;
+	}
+	iters = it; last_diff = diff;
+	sp.abundance_len.clear();
+	for(std::map<uint64_t, uint64_t>::iterator i = t2n.begin(); i != t2n.end(); ++i) sp.abundance_len[i->first] = p[i->second];
+}
+
+// ------------------------------------------------------------------------------ formatting
+struct Lcg {           // RandomSource random_source.h:34-61
+	uint32_t last;
+	inline uint32_t next() { last = 1664525u * last + 1013904223u; uint32_t r = last >> 16; last = 1664525u * last + 1013904223u; return r ^ last; }
+};
+
+static inline char* put_u64(char* p, uint64_t v) {
+	char tmp[24]; int n = 0;
+	do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while(v);
+	while(n) *p++ = tmp[--n];
+	return p;
+}
+
+struct Formatter {
+	const HostIndex& h; const Options& o; Species& sp;
+	std::vector<char> out;
+	std::vector<std::pair<int64_t, uint32_t> > buf;
+	Formatter(const HostIndex& h_, const Options& o_, Species& s) : h(h_), o(o_), sp(s) {}
+
+	void format_batch(const HostBatch& hb, const cfb_result& res) {
+		out.clear();
+		for(size_t u = 0; u < hb.n; u++) {
+			const uint32_t r0 = res.rec_off[u], r1 = res.rec_off[u + 1];
+			const uint32_t sz = r1 > r0 ? r1 - r0 : 1;
+			const bool uncl = r1 == r0;
+			const uint8_t fl = hb.flags[u];
+			const bool f1 = fl & 1, f2 = (fl & 2) != 0;
+			// max score of the mates that were classified (classifier.h:530-535); 0 for "unclassified"
+			int64_t max_score = 0;
+			if(!uncl) {
+				if(f1) { const int64_t L = hb.len[0][u]; max_score += L > 15 ? (L - 15) * (L - 15) : 0; }
+				if(f2) { const int64_t L = hb.len[1][u]; max_score += L > 15 ? (L - 15) * (L - 15) : 0; }
+			}
+			Lcg rnd; rnd.last = (f1 && f2) ? (hb.seedA[u] ^ hb.seedB[u]) : hb.seedA[u];   // centrifuge.cpp:2609-2613
+			// AlnSetSumm::init aligner_result.h:398-427
+			const int64_t INV = std::numeric_limits<int64_t>::min();
+			int64_t best = INV, sec = INV;
+			buf.resize(sz);
+			for(uint32_t k = 0; k < sz; k++) {
+				const int64_t sc = uncl ? 0 : (int64_t)res.recs[r0 + k].score;
+				if(sc > best) { sec = best; best = sc; } else if(sc > sec) sec = sc;
+				buf[k] = std::make_pair(sc, k);
+			}
+			// selectByScore aln_sink.h:1861-1927
+			size_t num = std::min<size_t>(sz, (size_t)o.prm.khits);
+			if(sz > 1) {
+				std::sort(buf.begin(), buf.end()); std::reverse(buf.begin(), buf.end());
+				size_t streak = 0;
+				for(size_t k = 1; k < sz; k++) {
+					if(buf[k].first == buf[k - 1].first) { if(streak == 0) streak = 1; streak++; }
+					else { if(streak > 1) shuffle(k - streak, streak, rnd); streak = 0; }
+				}
+				if(streak > 1) shuffle(sz - streak, streak, rnd);
+				for(size_t k = 0; k + 1 < num; k++) if(buf[k].first != buf[k + 1].first) { num = k + 1; break; }
+			}
+			const uint64_t qlen = (uint64_t)hb.len[0][u] + (hb.paired ? hb.len[1][u] : 0);
+			const char* nm = hb.names.data() + hb.name_off[u];
+			size_t nlen = (u + 1 < hb.n ? hb.name_off[u + 1] : hb.names.size()) - hb.name_off[u];
+			if(nlen >= 2 && nm[nlen - 2] == '/' && (nm[nlen - 1] == '1' || nm[nlen - 1] == '2' || nm[nlen - 1] == '3')) nlen -= 2;   // appendReadID aln_sink.h:2202
+			size_t idlen = 0; while(idlen < nlen && !isspace((unsigned char)nm[idlen])) idlen++;
+			for(size_t k = 0; k < num; k++) {
+				const size_t base = out.size();
+				out.resize(base + idlen + 512);
+				char* p = out.data() + base;
+				memcpy(p, nm, idlen); p += idlen; *p++ = '\t';
+				uint64_t taxid = 0, score = 0, hitlen = 0; uint32_t uid = CFB_UID_NONE;
+				if(!uncl) { const cfb_rec& r = res.recs[r0 + buf[k].second]; taxid = r.taxid; score = r.score; hitlen = r.hitlen; uid = r.uid; }
+				// seqID: appendSeqID aln_sink.h:2220-2234 on top of the uid chosen at classifier.h:557
+				const char* sid;
+				if(uncl) sid = "unclassified";
+				else {
+					const TaxNode* n = h.find_node(taxid);
+					const bool leaf = n ? n->leaf != 0 : true; const int rank = n ? n->rank : RANK_UNKNOWN;
+					sid = (leaf && uid != CFB_UID_NONE && uid < h.seq_name.size()) ? h.seq_name[uid].c_str() : rank_name(rank);
+				}
+				size_t sl = strlen(sid);
+				if(sl > 400) { const size_t used = p - (out.data() + base); out.resize(base + used + sl + 256); p = out.data() + base + used; }
+				memcpy(p, sid, sl); p += sl; *p++ = '\t';
+				p = put_u64(p, taxid & 0xffffffffull);                         // appendTaxID aln_sink.h:2237-2250
+				if(taxid >> 32) { *p++ = '.'; p = put_u64(p, taxid >> 32); }
+				*p++ = '\t'; p = put_u64(p, score);
+				*p++ = '\t'; p = put_u64(p, sec != INV ? (uint64_t)sec : 0);
+				*p++ = '\t'; p = put_u64(p, hitlen);
+				*p++ = '\t'; p = put_u64(p, qlen);
+				*p++ = '\t'; p = put_u64(p, (uint64_t)num);
+				*p++ = '\n';
+				out.resize(p - out.data());
+				sp.add(taxid, (int64_t)score, max_score, (uint32_t)num);
+			}
+		}
+	}
+	inline void shuffle(size_t begin, size_t n, Lcg& rnd) {    // EList::shufflePortion ds.h:784-795
+		size_t left = n;
+		for(size_t i = begin; i < begin + n - 1; i++) { const uint32_t r = rnd.next() % left; if(r > 0) std::swap(buf[i], buf[i + r]); left--; }
+	}
+};
+
+static void write_report(const HostIndex& h, const Options& o, Species& sp) {   // centrifuge.cpp:3231-3319
+	std::cerr << "report file " << o.report << std::endl;
+	std::ofstream ro(o.report.c_str());
+	if(o.abundance) {
+		size_t iters = 0; double diff = 0.0;
+		calc_abundance(h, sp, iters, diff);
+		std::cerr << "Number of iterations in EM algorithm: " << iters << std::endl;
+		std::cerr << "Probability diff. (P - P_prev) in the last iteration: " << diff << std::endl;
+	}
+	ro << "name\ttaxID\ttaxRank\tgenomeSize\tnumReads\tnumUniqueReads\tabundance" << std::endl;
+	for(std::map<uint64_t, Counts>::const_iterator it = sp.counts.begin(); it != sp.counts.end(); ++it) {
+		const uint64_t taxid = it->first;
+		if(taxid == 0) continue;
+		std::map<uint64_t, std::string>::const_iterator nm = h.names.find(taxid);
+		if(nm != h.names.end()) ro << nm->second; else ro << taxid;
+		ro << '\t' << taxid << '\t';
+		const TaxNode* n = h.find_node(taxid);
+		const int rank = n ? n->rank : 0; const bool leaf = n ? n->leaf != 0 : false;
+		if(rank == RANK_UNKNOWN && leaf) ro << "leaf"; else ro << rank_name(rank);
+		ro << '\t';
+		std::map<uint64_t, uint64_t>::const_iterator s = h.sizes.find(taxid);
+		ro << (s != h.sizes.end() ? s->second : 0) << '\t' << it->second.n_reads << '\t' << it->second.n_unique << '\t';
+		std::map<uint64_t, double>::const_iterator ab = sp.abundance_len.find(taxid);
+		if(ab != sp.abundance_len.end()) ro << ab->second; else ro << "0.0";
+		ro << std::endl;
+	}
+}
+
+static void print_arg_desc() {            // same shape as printArgDesc centrifuge.cpp:701-732
+	for(const OptDesc* d = kLong; d->name; d++) std::cout << d->name << "\t" << d->has_arg << std::endl;
+	const size_t n = strlen(kShort);
+	for(size_t i = 0; i < n; i++) {
+		if(i + 1 < n && kShort[i + 1] == ':') { std::cout << kShort[i] << "\t" << 1 << std::endl; i++; }
+		else std::cout << kShort[i] << "\t" << 0 << std::endl;
+	}
+}
+
+static int parse_args(int argc, const char** argv, Options& o, bool& exit_now) {
+	cfb_params_default(&o.prm);
+	exit_now = false;
+	std::string rank_name_arg = "strain";
+	for(int i = 1; i < argc; i++) {
+		std::string a = argv[i];
+		std::string key; bool is_long = false;
+		if(a.size() > 2 && a[0] == '-' && a[1] == '-') { key = a.substr(2); is_long = true; }
+		else if(a.size() >= 2 && a[0] == '-') key = a.substr(1, 1);
+		else {   // positional: <index> then reads, as the reference's getopt tail does (centrifuge.cpp:1628-1660)
+			if(o.index.empty()) o.index = a; else { std::vector<std::string> v = split(a, ','); o.singles.insert(o.singles.end(), v.begin(), v.end()); }
+			continue;
+		}
+		std::string val; bool has_val = false;
+		if(is_long) { size_t eq = key.find('='); if(eq != std::string::npos) { val = key.substr(eq + 1); key = key.substr(0, eq); has_val = true; } }
+		else if(a.size() > 2) { val = a.substr(2); has_val = true; }
+		int need = -1;
+		if(is_long) { for(const OptDesc* d = kLong; d->name; d++) if(key == d->name) need = d->has_arg; }
+		else { const char* q = strchr(kShort, key[0]); if(q && key[0] != ':') need = q[1] == ':' ? 1 : 0; }
+		if(need < 0) { std::cerr << "centrifuge-class: unrecognized option '" << a << "'" << std::endl; return 1; }
+		if(need == 1 && !has_val) { if(i + 1 >= argc) { std::cerr << "centrifuge-class: option '" << a << "' requires an argument" << std::endl; return 1; } val = argv[++i]; }
+		if(key == "x") o.index = val;
+		else if(key == "U") { std::vector<std::string> v = split(val, ','); o.singles.insert(o.singles.end(), v.begin(), v.end()); }
+		else if(key == "1") { std::vector<std::string> v = split(val, ','); o.mates1.insert(o.mates1.end(), v.begin(), v.end()); }
+		else if(key == "2") { std::vector<std::string> v = split(val, ','); o.mates2.insert(o.mates2.end(), v.begin(), v.end()); }
+		else if(key == "f") o.fasta = true; else if(key == "q") o.fasta = false;
+		else if(key == "S") o.out = val; else if(key == "report-file") o.report = val;
+		else if(key == "k") { o.prm.khits = atoi(val.c_str()); if(o.prm.khits < 1) { std::cerr << "-k arg must be at least 1" << std::endl; return 1; } }
+		else if(key == "min-hitlen") { o.prm.min_hitlen = atoi(val.c_str()); if(o.prm.min_hitlen < 15) { std::cerr << "--min-hitlen arg must be at least 15" << std::endl; return 1; } }
+		else if(key == "host-taxids") { std::vector<std::string> v = split(val, ','); for(size_t k = 0; k < v.size(); k++) o.host.push_back(strtoull(v[k].c_str(), NULL, 10)); }
+		else if(key == "exclude-taxids") { std::vector<std::string> v = split(val, ','); for(size_t k = 0; k < v.size(); k++) o.excl.push_back(strtoull(v[k].c_str(), NULL, 10)); }
+		else if(key == "no-traverse") o.prm.tree_traverse = 0;
+		else if(key == "classification-rank") rank_name_arg = val;
+		else if(key == "no-abundance") o.abundance = false;
+		else if(key == "p" || key == "threads" || key == "wrapper") { /* host threads are managed internally */ }
+		else if(key == "reorder" || key == "mm") { /* output is always in input order; index is always resident in HBM */ }
+		else if(key == "t" || key == "time") o.time = true;
+		else if(key == "quiet") o.quiet = true;
+		else if(key == "seed") o.seed = (uint32_t)strtoul(val.c_str(), NULL, 10);
+		else if(key == "u" || key == "upto" || key == "qupto") o.upto = strtoull(val.c_str(), NULL, 10);
+		else if(key == "s" || key == "skip") o.skip = strtoull(val.c_str(), NULL, 10);
+		else if(key == "5" || key == "trim5") o.trim5 = atoi(val.c_str());
+		else if(key == "3" || key == "trim3") o.trim3 = atoi(val.c_str());
+		else if(key == "device") o.device = atoi(val.c_str());
+		else if(key == "batch-units") o.batch_units = (size_t)strtoull(val.c_str(), NULL, 10);
+		else if(key == "arg-desc") { print_arg_desc(); exit_now = true; return 0; }
+		else if(key == "version") { std::cout << "centrifuge-class (cfb200, B200-native) compatible with Centrifuge 1.0.4" << std::endl; exit_now = true; return 0; }
+		else if(key == "h" || key == "help") { std::cout << "Usage: centrifuge-class [options]* -x <cf-idx> {-1 <m1> -2 <m2> | -U <r>} [-S <out.tsv>] [--report-file <report>]" << std::endl; exit_now = true; return 0; }
+	}
+	o.prm.class_rank_slot = rank_to_slot(rank_from_name(rank_name_arg.c_str()));
+	o.prm.host_taxids = o.host.data(); o.prm.n_host_taxids = o.host.size();
+	o.prm.excluded_taxids = o.excl.data(); o.prm.n_excluded_taxids = o.excl.size();
+	if(o.index.empty()) { std::cerr << "No index, query, or output file specified!" << std::endl; return 1; }
+	if(o.mates1.size() != o.mates2.size()) { std::cerr << "Error: " << o.mates1.size() << " mate files/sequences were specified with -1, but " << o.mates2.size() << std::endl << "mate files/sequences were specified with -2.  The same number of mate files/" << std::endl << "sequences must be specified with -1 and -2." << std::endl; return 1; }
+	if(o.singles.empty() && o.mates1.empty()) { std::cerr << "No index, query, or output file specified!" << std::endl; return 1; }
+	if(o.batch_units < 1) o.batch_units = 1;
+	return 0;
+}
+
+}  // namespace
+
+extern "C" int cfb_run(int argc, const char** argv) {
+	init_tables();
+	Options o; bool exit_now = false;
+	try {
+		int rc = parse_args(argc, argv, o, exit_now);
+		if(rc || exit_now) return rc;
+		cfb_index* ix = NULL;
+		if(cfb_index_load(o.index.c_str(), o.device, &ix) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; return 1; }
+		cfb_ctx* ctx = NULL;
+		if(cfb_ctx_create(ix, &o.prm, &ctx) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; cfb_index_free(ix); return 1; }
+		const HostIndex& h = *cfb_index_host(ix);
+		FILE* fo = o.out == "-" ? stdout : fopen(o.out.c_str(), "wb");
+		if(!fo) { std::cerr << "Error: could not open output file " << o.out << std::endl; return 1; }
+		fputs("readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n", fo);
+		Species sp; Formatter fmt(h, o, sp);
+		const int nslots = cfb_ctx_slots(ctx);
+		std::vector<HostBatch> hb(nslots);
+		std::vector<bool> busy(nslots, false);
+		int cur = 0; uint64_t rdid = 0;
+		bool failed = false;
+		auto drain = [&](int s) -> bool {
+			cfb_result res;
+			if(cfb_classify_wait(ctx, s, &res) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; return false; }
+			fmt.format_batch(hb[s], res);
+			if(!fmt.out.empty()) fwrite(fmt.out.data(), 1, fmt.out.size(), fo);
+			busy[s] = false;
+			return true;
+		};
+		auto flush = [&](int s) -> bool {
+			if(hb[s].n == 0) return true;
+			cfb_batch b; memset(&b, 0, sizeof b);
+			b.n_units = hb[s].n; b.n_mates = hb[s].paired ? 2 : 1; b.bases = hb[s].bases.data(); b.n_bases = hb[s].bases.size();
+			b.off[0] = hb[s].off[0].data(); b.len[0] = hb[s].len[0].data();
+			if(hb[s].paired) { b.off[1] = hb[s].off[1].data(); b.len[1] = hb[s].len[1].data(); }
+			b.flags = hb[s].flags.data();
+			if(cfb_classify_submit(ctx, s, &b) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; return false; }
+			busy[s] = true;
+			return true;
+		};
+		// all files in the reference's order: paired sources first? No: PairedDualPatternSource walks
+		// srca_ in the order {mates1..., singles...} (pat.cpp:330-420: m12, m1/m2, then singles)
+		struct Src { std::string a, b; bool paired; };
+		std::vector<Src> srcs;
+		for(size_t i = 0; i < o.mates1.size(); i++) { Src s; s.a = o.mates1[i]; s.b = o.mates2[i]; s.paired = true; srcs.push_back(s); }
+		for(size_t i = 0; i < o.singles.size(); i++) { Src s; s.a = o.singles[i]; s.paired = false; srcs.push_back(s); }
+		bool stop = false;
+		for(size_t si = 0; si < srcs.size() && !failed && !stop; si++) {
+			FileIn fa, fb;
+			if(!fa.open(srcs[si].a)) { std::cerr << "Warning: Could not open read file \"" << srcs[si].a << "\" for reading; skipping..." << std::endl; continue; }
+			if(srcs[si].paired && !fb.open(srcs[si].b)) { std::cerr << "Warning: Could not open read file \"" << srcs[si].b << "\" for reading; skipping..." << std::endl; continue; }
+			bool firstA = true, firstB = true; uint64_t cntA = 0, cntB = 0;
+			Rec ra, rb;
+			hb[cur].clear(srcs[si].paired);
+			for(;;) {
+				const bool okA = o.fasta ? parse_fasta(fa, ra, cntA, firstA, o.trim5, o.trim3) : parse_fastq(fa, ra, cntA, firstA, o.trim5, o.trim3);
+				bool okB = true;
+				if(srcs[si].paired) okB = o.fasta ? parse_fasta(fb, rb, cntB, firstB, o.trim5, o.trim3) : parse_fastq(fb, rb, cntB, firstB, o.trim5, o.trim3);
+				if(!okA && srcs[si].paired && okB) { std::cerr << "Error, fewer reads in file specified with -1 than in file specified with -2" << std::endl; throw 1; }
+				if(!okA) break;
+				if(!okB) { std::cerr << "Error, fewer reads in file specified with -2 than in file specified with -1" << std::endl; throw 1; }
+				// empty reads are kept: the reference reports them as length-filtered "unclassified" rows
+				const uint64_t id = rdid++;
+				if(id >= o.upto) { stop = true; break; }
+				if(id < o.skip) continue;
+				hb[cur].add(ra, srcs[si].paired ? &rb : NULL, o.seed);
+				if(hb[cur].n >= o.batch_units) {
+					if(!flush(cur)) { failed = true; break; }
+					const int nxt = (cur + 1) % nslots;
+					if(busy[nxt] && !drain(nxt)) { failed = true; break; }
+					cur = nxt; hb[cur].clear(srcs[si].paired);
+				}
+			}
+			fa.close(); fb.close();
+			if(failed) break;
+			// finish this source: submit the partial batch, then drain everything in submission order
+			if(!flush(cur)) { failed = true; break; }
+			for(int k = 1; k <= nslots; k++) { const int s = (cur + k) % nslots; if(busy[s] && !drain(s)) { failed = true; break; } }
+			hb[cur].clear(false);
+		}
+		if(fo != stdout) fclose(fo); else fflush(stdout);
+		if(!failed && !o.report.empty()) write_report(h, o, sp);
+		cfb_ctx_destroy(ctx); cfb_index_free(ix);
+		return failed ? 1 : 0;
+	} catch(int e) {
+		return e ? e : 1;
+	} catch(std::exception& e) {
+		std::cerr << "Error: Encountered exception: '" << e.what() << "'" << std::endl;
+		return 1;
+	}
+}

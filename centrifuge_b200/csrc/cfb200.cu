@@ -579,6 +579,8 @@ extern "C" int cfb_index_tax_node(const cfb_index* ix, uint64_t taxid, uint64_t*
 	if(parent) *parent = n->parent; if(rank) *rank = n->rank; if(leaf) *leaf = n->leaf;
 	return 1;
 }
+// internal accessor for the host driver (cf_host.cpp); not part of the public C ABI
+extern "C" const cfb::HostIndex* cfb_index_host(const cfb_index* ix) { return ix ? &ix->h : NULL; }
 extern "C" void cfb_params_default(cfb_params* p) {
 	if(!p) return;
 	memset(p, 0, sizeof *p); p->khits = 5; p->min_hitlen = 22; p->tree_traverse = 1; p->class_rank_slot = 0;

@@ -1119,7 +1119,6 @@ extern "C" int cfo_main(int argc, const char** argv) {
 		if(!okA) break;
 		cntA++;
 		if(paired) { bool okB = fasta ? read_fasta(*fbp, rb, cntB, firstB, emptyB) : read_fastq(*fbp, rb, cntB, firstB); if(!okB) break; cntB++; }
-		if(ra.seq.empty()) continue;                        // reference: success with empty read => nextReadPair loops
 		u32 seedA = gen_rand_seed(ra, 0), seedB = paired ? gen_rand_seed(rb, 0) : 0;
 		bool pair = paired && !rb.seq.empty();
 		bool f1 = n_filter(ra.seq) && ra.seq.size() >= 2, f2 = pair ? (n_filter(rb.seq) && rb.seq.size() >= 2) : false;

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+
+
+@pytest.fixture(scope="session")
+def adv_base():
+    import util
+    return util.golden_index("adv")
+
+
+@pytest.fixture(scope="session")
+def adv_reads():
+    import lzma
+    import util
+    p = os.path.join(util.CACHE, "golden", "adv.reads.fa")
+    os.makedirs(os.path.dirname(p), exist_ok=True)
+    with lzma.open(os.path.join(util.GOLDEN, "adv.reads.fa.xz")) as f, open(p, "wb") as g:
+        g.write(f.read())
+    return p

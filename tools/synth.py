@@ -141,6 +141,101 @@ def sample_pairs(seqs, n, rdlen, seed, sub=0.01, nrate=0.001, random_frac=0.05,
     return out
 
 
+def rc_codes(x):
+    return (3 - x)[::-1]
+
+
+def write_adversarial(outdir, seed=33, n_reads=3000):
+    """Small index + reads that exercise the rare branches of the classifier:
+    inverted repeats (both strands hit => extend / twin-removal), tandem and homopolymer
+    repeats (SA ranges larger than ihits), a 300-copy dispersed repeat, `cid` sequence names
+    (compressed-index ihits rule), N-rich / very short / IUPAC reads, names with spaces."""
+    os.makedirs(outdir, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    seqs = []
+    base = rng.integers(0, 4, size=60000, dtype=np.uint8)
+    seqs.append(base)
+    seqs.append(rc_codes(base))
+    m = base.copy()
+    mask = rng.random(len(m)) < 0.02
+    m[mask] = (m[mask] + 1) & 3
+    seqs.append(m)
+    seqs.append(rc_codes(m[10000:40000]))
+    unit = rng.integers(0, 4, size=7, dtype=np.uint8)
+    seqs.append(np.concatenate([rng.integers(0, 4, size=5000, dtype=np.uint8), np.tile(unit, 800),
+                                rng.integers(0, 4, size=5000, dtype=np.uint8)]))
+    seqs.append(np.concatenate([np.zeros(3000, dtype=np.uint8), rng.integers(0, 4, size=3000, dtype=np.uint8),
+                                np.full(3000, 3, dtype=np.uint8)]))
+    rep = rng.integers(0, 4, size=150, dtype=np.uint8)
+    parts = []
+    for _ in range(300):
+        parts.append(rng.integers(0, 4, size=200, dtype=np.uint8))
+        parts.append(rep)
+    seqs.append(np.concatenate(parts))
+    rep2 = rng.integers(0, 4, size=120, dtype=np.uint8)
+    parts = []
+    for _ in range(30):
+        parts.append(rng.integers(0, 4, size=300, dtype=np.uint8))
+        parts.append(rep2)
+    seqs.append(np.concatenate(parts))
+    for _ in range(12):
+        seqs.append(rng.integers(0, 4, size=4000, dtype=np.uint8))
+    n = len(seqs)
+    with open(os.path.join(outdir, "genomes.fa"), "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b">cid%d\n" % i)
+            f.write(ACGT[s].tobytes() + b"\n")
+    with open(os.path.join(outdir, "conv.tsv"), "w") as f:
+        for i in range(n):
+            f.write("cid%d\t%d\n" % (i, 1000 + i))
+    with open(os.path.join(outdir, "nodes.dmp"), "w") as f:
+        f.write("1\t|\t1\t|\tno rank\t|\n")
+        f.write("10\t|\t1\t|\tfamily\t|\n11\t|\t1\t|\tfamily\t|\n")
+        for g in range(4):
+            f.write("%d\t|\t%d\t|\tgenus\t|\n" % (100 + g, 10 + g % 2))
+        for i in range(n):
+            f.write("%d\t|\t%d\t|\tspecies\t|\n" % (1000 + i, 100 + i % 4))
+    with open(os.path.join(outdir, "names.dmp"), "w") as f:
+        f.write("1\t|\troot\t|\t\t|\tscientific name\t|\n")
+        for t in (10, 11):
+            f.write("%d\t|\tFam%d\t|\t\t|\tscientific name\t|\n" % (t, t))
+        for g in range(4):
+            f.write("%d\t|\tGen%d\t|\t\t|\tscientific name\t|\n" % (100 + g, g))
+        for i in range(n):
+            f.write("%d\t|\tSp %d\t|\t\t|\tscientific name\t|\n" % (1000 + i, i))
+    reads = []
+    for k in range(n_reads):
+        si = int(rng.integers(0, n))
+        s = seqs[si]
+        L = min(int(rng.integers(20, 260)), len(s))
+        p = int(rng.integers(0, len(s) - L + 1))
+        r = s[p:p + L].copy()
+        mm = rng.random(L) < 0.02
+        r[mm] = (r[mm] + 1) & 3
+        if rng.random() < 0.5:
+            r = rc_codes(r)
+        a = ACGT[r].copy()
+        u = rng.random()
+        if u < 0.15:
+            a[rng.random(L) < 0.05] = ord("N")
+        elif u < 0.2:
+            a[rng.random(L) < 0.2] = ord("N")
+        reads.append(("x%d" % k, a))
+    s0 = seqs[0]
+    for nm, a in (("short1", s0[:1]), ("short5", s0[:5]), ("short9", s0[:9]), ("short10", s0[:10]),
+                  ("short21", s0[:21]), ("short22", s0[100:122]), ("short23", s0[100:123])):
+        reads.append((nm, ACGT[a].copy()))
+    reads.append(("allN", np.full(50, ord("N"), dtype=np.uint8)))
+    reads.append(("polyA", np.full(100, ord("A"), dtype=np.uint8)))
+    reads.append(("polyT", np.full(100, ord("T"), dtype=np.uint8)))
+    reads.append(("iupac", np.frombuffer(b"ACGTRYKMACGTACGTNNACGTTTGGCCAAXBDHVACGTACGTAGCTAGCTAGCTAGCATCGATCGACTAGC", dtype=np.uint8).copy()))
+    reads.append(("name with space/1", ACGT[seqs[2][500:600]].copy()))
+    reads.append(("pal", np.concatenate([ACGT[s0[200:260]], ACGT[rc_codes(s0[200:260])]])))
+    write_fasta(os.path.join(outdir, "reads.fa"), reads)
+    write_fastq(os.path.join(outdir, "reads.fq"), reads, qual=b"5")
+    return seqs, reads
+
+
 def write_fasta(path, reads):
     with open(path, "wb") as f:
         for name, a in reads:
