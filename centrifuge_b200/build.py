@@ -17,10 +17,11 @@ CLI = os.path.join(HERE, "centrifuge-class")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-Wno-deprecated-declarations", "--expt-relaxed-constexpr",
+    "-Wno-deprecated-gpu-targets", "-diag-suppress", "1444",
 ]
 
-LIB_SOURCES = ["cfb200.cu", "cf_index.cpp", "cf_host.cpp"]
+LIB_SOURCES = ["cfb200.cu", "cf_build.cu", "cf_index.cpp", "cf_host.cpp"]
 CLI_SOURCES = ["cf_cli.cpp"]
 
 

@@ -199,3 +199,74 @@ def test_resolve(index, rows):
     out = np.zeros(len(rows), dtype=np.uint32)
     _ck(lib().cfb_test_resolve(index.h, _p(rows, C.c_uint64), C.c_uint64(len(rows)), _p(out, C.c_uint32)))
     return out
+
+
+class BuildOpts(C.Structure):
+    _fields_ = [("out_base", C.c_char_p), ("fasta", C.POINTER(C.c_char_p)), ("n_fasta", C.c_int32),
+                ("synth_genera", C.c_uint32), ("synth_species", C.c_uint32), ("synth_len", C.c_uint64), ("synth_seed", C.c_uint64),
+                ("synth_div", C.c_double), ("conversion_table", C.c_char_p), ("taxonomy_tree", C.c_char_p), ("name_table", C.c_char_p),
+                ("size_table", C.c_char_p), ("ftab_chars", C.c_int32), ("off_rate", C.c_int32), ("device", C.c_int32), ("verbose", C.c_int32)]
+
+
+def build_opts(out_base=None, fasta=(), synth=None, conversion_table=None, taxonomy_tree=None, name_table=None, size_table=None,
+               ftab_chars=10, off_rate=4, device=0, verbose=0):
+    """synth = (genera, species, len, seed, div) for counter-based synthetic genomes."""
+    o = BuildOpts()
+    lib().cfb_build_opts_default(C.byref(o))
+    o.out_base = out_base.encode() if out_base else None
+    if fasta:
+        o._fa = (C.c_char_p * len(fasta))(*[f.encode() for f in fasta])
+        o.fasta, o.n_fasta = C.cast(o._fa, C.POINTER(C.c_char_p)), len(fasta)
+    if synth:
+        o.synth_genera, o.synth_species, o.synth_len, o.synth_seed, o.synth_div = synth
+    for k, v in (("conversion_table", conversion_table), ("taxonomy_tree", taxonomy_tree), ("name_table", name_table), ("size_table", size_table)):
+        if v:
+            setattr(o, k, v.encode())
+    o.ftab_chars, o.off_rate, o.device, o.verbose = ftab_chars, off_rate, device, verbose
+    return o
+
+
+def build_index(opts):
+    L = lib()
+    L.cfb_build_last_error.restype = C.c_char_p
+    rc = L.cfb_build_index(C.byref(opts))
+    if rc != 0:
+        raise CfbError("cfb_build_index error %d: %s" % (rc, L.cfb_build_last_error().decode()))
+
+
+def synth_reads(opts, n, rdlen, seed):
+    out = np.zeros((n, rdlen), dtype=np.uint8)
+    L = lib()
+    L.cfb_build_last_error.restype = C.c_char_p
+    rc = L.cfb_synth_reads(C.byref(opts), C.c_uint64(n), C.c_uint32(rdlen), C.c_uint64(seed), _p(out, C.c_uint8))
+    if rc != 0:
+        raise CfbError("cfb_synth_reads error %d: %s" % (rc, L.cfb_build_last_error().decode()))
+    return out
+
+
+def synth_fasta(opts, path):
+    rc = lib().cfb_synth_fasta(C.byref(opts), path.encode())
+    if rc != 0:
+        raise CfbError("cfb_synth_fasta failed")
+
+
+def write_synth_taxonomy(outdir, genera, species, length):
+    """conversion table / nodes.dmp / names.dmp of the synthetic recipe (same as tools/synth.py)."""
+    os.makedirs(outdir, exist_ok=True)
+    n = genera * species
+    with open(os.path.join(outdir, "conv.tsv"), "w") as f:
+        for i in range(n):
+            f.write("seq%d\t%d\n" % (i, 1000 + i))
+    with open(os.path.join(outdir, "nodes.dmp"), "w") as f:
+        f.write("1\t|\t1\t|\tno rank\t|\n")
+        for g in range(genera):
+            f.write("%d\t|\t1\t|\tgenus\t|\n" % (100 + g))
+        for i in range(n):
+            f.write("%d\t|\t%d\t|\tspecies\t|\n" % (1000 + i, 100 + i // species))
+    with open(os.path.join(outdir, "names.dmp"), "w") as f:
+        f.write("1\t|\troot\t|\t\t|\tscientific name\t|\n")
+        for g in range(genera):
+            f.write("%d\t|\tGenus%d\t|\t\t|\tscientific name\t|\n" % (100 + g, g))
+        for i in range(n):
+            f.write("%d\t|\tGenus%d species%d\t|\t\t|\tscientific name\t|\n" % (1000 + i, i // species, i))
+    return (os.path.join(outdir, "conv.tsv"), os.path.join(outdir, "nodes.dmp"), os.path.join(outdir, "names.dmp"))

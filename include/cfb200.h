@@ -149,6 +149,31 @@ int cfb_test_resolve(const cfb_index*, const uint64_t* rows, uint64_t n, uint32_
 const char* cfb_last_error(void);
 const char* cfb_version(void);
 
+/* ---- index builder (libcfb200): GPU construction of `.1-.4.cf` ----------------------------
+ * Replaces: centrifuge-build-bin (centrifuge_build.cpp:472-560 -> Ebwt::initFromVector /
+ * buildToDisk, bt2_idx.h:1247-1640,3379-3840) for lineRate 7 indexes.  Either FASTA inputs, or
+ * (n_fasta == 0) counter-based synthetic genomes "seq0..seqN-1" of synth_genera x synth_species
+ * sequences of synth_len bases generated on the device (cf_synth.h) -- used by bench.py to obtain a
+ * p_compressed-scale index without network access. */
+typedef struct {
+	const char* out_base;
+	const char* const* fasta; int32_t n_fasta;
+	uint32_t synth_genera, synth_species; uint64_t synth_len, synth_seed; double synth_div;
+	const char* conversion_table;   /* --conversion-table */
+	const char* taxonomy_tree;      /* --taxonomy-tree (nodes.dmp) */
+	const char* name_table;         /* --name-table (names.dmp), may be NULL */
+	const char* size_table;         /* --size-table, may be NULL */
+	int32_t ftab_chars, off_rate;   /* defaults 10, 4 (centrifuge_build.cpp:93-97) */
+	int32_t device, verbose;
+} cfb_build_opts;
+void cfb_build_opts_default(cfb_build_opts*);
+int  cfb_build_index(const cfb_build_opts*);
+const char* cfb_build_last_error(void);
+/* n reads of rdlen bases (codes 0..4) sampled from the synthetic genomes of `o`: uniform sequence /
+ * position / strand, 1% substitutions, 0.1% N, 5% random reads (SURVEY.md 8d recipe). */
+int cfb_synth_reads(const cfb_build_opts* o, uint64_t n, uint32_t rdlen, uint64_t read_seed, uint8_t* out_codes);
+int cfb_synth_fasta(const cfb_build_opts* o, const char* path);
+
 /* ---- host driver (libcfb200_host): drop-in for `centrifuge-class` ------------------
  * Replaces: extern "C" int centrifuge(int argc, const char** argv) (centrifuge.cpp:3345).
  * Same argv conventions and exit codes for the options it implements; unknown options
