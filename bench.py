@@ -40,49 +40,37 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------ workload
-def workload_genomes(genera, species, length, seed):
-    import synth
-    return synth.make_genomes(genera, species, length, seed)
+def synth_opts(genera, species, length, seed, base=None, device=0, tax=None):
+    from centrifuge_b200 import capi
+    kw = {}
+    if tax:
+        kw = dict(conversion_table=tax[0], taxonomy_tree=tax[1], name_table=tax[2])
+    return capi.build_opts(base, synth=(genera, species, length, seed, 0.03), device=device, **kw)
 
 
-def get_index(genera, species, length, seed):
-    """Synthetic index on local disk (built once per box)."""
+def get_index(genera, species, length, seed, device=0):
+    """Synthetic p_compressed-class index on local disk, built once per box by the GPU builder
+    (centrifuge_b200/csrc/cf_build.cu; byte-identical to centrifuge-build-bin, tests/test_gpu_build.py)."""
+    from centrifuge_b200 import capi
     tag = "g%d_s%d_l%d_seed%d" % (genera, species, length, seed)
     d = os.path.join(CACHE, tag)
     base = os.path.join(d, "idx")
-    if os.path.exists(base + ".4.cf") and os.path.exists(os.path.join(d, "done")):
+    if os.path.exists(os.path.join(d, "done")):
         return base, d
     os.makedirs(d, exist_ok=True)
-    import synth
     t0 = time.time()
-    synth.write_genomes(d, genera, species, length, seed)
-    ncpu = os.cpu_count() or 8
-    with open(os.path.join(d, "build.log"), "w") as lg:
-        subprocess.check_call([REF_BUILD, "-p", str(min(ncpu, 64)), "--conversion-table", os.path.join(d, "conv.tsv"),
-                               "--taxonomy-tree", os.path.join(d, "nodes.dmp"), "--name-table", os.path.join(d, "names.dmp"),
-                               os.path.join(d, "genomes.fa"), base], stdout=lg, stderr=lg)
+    tax = capi.write_synth_taxonomy(d, genera, species, length)
+    capi.build_index(synth_opts(genera, species, length, seed, base, device, tax))
     open(os.path.join(d, "done"), "w").close()
-    log("index %s built in %.1f s" % (tag, time.time() - t0))
+    log("index %s built on the GPU in %.1f s" % (tag, time.time() - t0))
     return base, d
 
 
-def make_reads(seqs, n, rdlen, seed):
-    """Vectorised sampler: uniform genome/position/strand, 1% substitutions, 0.1% N, 5% random reads.
+def make_reads(genera, species, length, gseed, n, rdlen, seed, device=0):
+    """cfb_synth_reads: uniform genome/position/strand, 1% substitutions, 0.1% N, 5% random reads.
     Returns codes (n, rdlen) uint8 in 0..4."""
-    rng = np.random.default_rng(seed)
-    G = np.stack(seqs)
-    L = G.shape[1]
-    si = rng.integers(0, G.shape[0], n)
-    pos = rng.integers(0, L - rdlen, n)
-    R = G[si[:, None], pos[:, None] + np.arange(rdlen)[None, :]]
-    sub = rng.random((n, rdlen)) < 0.01
-    R = np.where(sub, (R + 1) & 3, R).astype(np.uint8)
-    rc = rng.random(n) < 0.5
-    R[rc] = (3 - R[rc])[:, ::-1]
-    rnd = rng.random(n) < 0.05
-    R[rnd] = rng.integers(0, 4, size=(int(rnd.sum()), rdlen), dtype=np.uint8)
-    R[rng.random((n, rdlen)) < 0.001] = 4
-    return np.ascontiguousarray(R)
+    from centrifuge_b200 import capi
+    return capi.synth_reads(synth_opts(genera, species, length, gseed, device=device), n, rdlen, seed)
 
 
 def write_fastq(path, codes, prefix="r"):
@@ -159,11 +147,10 @@ def main():
         if rank != 0:
             return 0
         base, d = get_index(a.genera, a.species, a.genome_len, 12345)
-        seqs = workload_genomes(a.genera, a.species, a.genome_len, 12345)
         n = a.cpu_sample
         fq = os.path.join(d, "sample_%d.fq" % n)
         if not os.path.exists(fq):
-            write_fastq(fq, make_reads(seqs, n, a.rdlen, 999))
+            write_fastq(fq, make_reads(a.genera, a.species, a.genome_len, 12345, n, a.rdlen, 999))
         for _ in range(min(a.warmup, 1)):
             ref_reads_per_s(base, fq, ncores)
         t = [ref_reads_per_s(base, fq, ncores) for _ in range(a.steps)]
@@ -188,12 +175,11 @@ def main():
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
-        base, d = get_index(a.genera, a.species, a.genome_len, 12345)
+        base, d = get_index(a.genera, a.species, a.genome_len, 12345, local)
     if dist:
         dist.barrier()
-    base, d = get_index(a.genera, a.species, a.genome_len, 12345)
-    seqs = workload_genomes(a.genera, a.species, a.genome_len, 12345)
-    codes = make_reads(seqs, a.reads, a.rdlen, 1000 + rank)
+    base, d = get_index(a.genera, a.species, a.genome_len, 12345, local)
+    codes = make_reads(a.genera, a.species, a.genome_len, 12345, a.reads, a.rdlen, 1000 + rank, local)
     n = a.reads
     bases = codes.reshape(-1)
     lens = np.full(n, a.rdlen, dtype=np.uint32)
@@ -304,7 +290,7 @@ def main():
             ns = a.cpu_sample
             fq = os.path.join(d, "sample_%d.fq" % ns)
             if not os.path.exists(fq):
-                write_fastq(fq, make_reads(seqs, ns, a.rdlen, 999))
+                write_fastq(fq, make_reads(a.genera, a.species, a.genome_len, 12345, ns, a.rdlen, 999, local))
             tt = ref_reads_per_s(base, fq, ncores)
             out["cpu_baseline"] = {"value": ns / tt, "unit": "reads/s", "cores": ncores, "kind": "reference",
                                    "sample": "%d reads, centrifuge-class -p %d, FASTQ in, TSV to /dev/null, index load included (%.1f s)" % (ns, ncores, tt)}

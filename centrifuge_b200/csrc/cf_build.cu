@@ -51,21 +51,34 @@ __device__ __forceinline__ uint64_t window32(const uint64_t* t, uint64_t i) {
 }
 __device__ __forceinline__ int base_at(const uint64_t* t, uint64_t i) { return (int)((t[i >> 5] >> (62 - 2 * (i & 31))) & 3); }
 
-// sort key of suffix `pos` for the window starting d bases into the suffix: 29 bases (zero padded past
-// the end of the text) and, in the low bits, how much of the suffix is left -- a suffix that ends
-// inside the window sorts before every longer suffix with the same padded bases.
+// The reference's suffix order treats the end of the text as GREATER than any base ("prefixes are
+// lexicographically greater than their extensions", multikey_qsort.h:194-205,379).
+// Sort key of suffix `pos` for the window starting d bases into the suffix: 29 bases, positions past
+// the end padded with T (the largest base), and in the low bits a code that is 0 while the window is
+// completely inside the text and grows as the suffix gets shorter -- so a suffix that ends inside the
+// window sorts after every longer suffix with the same padded bases, shortest last.
 __device__ __forceinline__ uint64_t suffix_key(const uint64_t* t, uint64_t len, uint64_t pos, uint64_t d) {
 	const uint64_t R = len - pos;
-	uint64_t chars = 0;
-	if(R > d) chars = window32(t, pos + d) >> 6;
-	uint64_t code = 0;
-	if(R + 2 >= d) { code = R + 2 - d; if(code > 63) code = 63; }
-	return (chars << 6) | code;
+	uint64_t chars = (1ull << 58) - 1;
+	if(R > d) {
+		chars = window32(t, pos + d) >> 6;
+		const uint64_t r = R - d;
+		if(r < (uint64_t)kWin) chars |= (1ull << (2 * (kWin - r))) - 1;
+	}
+	uint64_t real = 0;
+	if(R + 2 >= d) { real = R + 2 - d; if(real > (uint64_t)kWin + 2) real = kWin + 2; }
+	return (chars << 6) | ((uint64_t)kWin + 2 - real);
+}
+// 2-base bucket of suffix i; a suffix of length 1 is padded with T
+__device__ __forceinline__ int bucket_of(const uint64_t* t, uint64_t len, uint64_t i) {
+	int b = (int)(window32(t, i) >> 60);
+	if(i + 1 >= len) b |= 3;
+	return b;
 }
 
 struct InBucket {
-	const uint64_t* t; int b;
-	__device__ __forceinline__ bool operator()(const uint64_t& i) const { return (int)(window32(t, i) >> 60) == b; }
+	const uint64_t* t; uint64_t len; int b;
+	__device__ __forceinline__ bool operator()(const uint64_t& i) const { return bucket_of(t, len, i) == b; }
 };
 
 __global__ void k_pack_text(const uint8_t* codes, uint64_t n, uint64_t* words, uint64_t nwords) {
@@ -90,7 +103,7 @@ __global__ void k_bucket_hist(const uint64_t* t, uint64_t len, unsigned long lon
 	if(threadIdx.x < 16) sh[threadIdx.x] = 0;
 	__syncthreads();
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) atomicAdd(&sh[window32(t, i) >> 60], 1u);
+	for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) atomicAdd(&sh[bucket_of(t, len, i)], 1u);
 	__syncthreads();
 	if(threadIdx.x < 16) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
@@ -500,7 +513,7 @@ extern "C" int cfb_build_index(const cfb_build_opts* o) {
 		cub::DoubleBuffer<uint32_t> dg(idx.p, idx.p);
 		cub::DeviceRadixSort::SortPairs(nullptr, tb, dg, dp, (int)cap, 0, 32); tmp_bytes = std::max(tmp_bytes, tb);
 		cub::CountingInputIterator<uint64_t> cit(0);
-		InBucket pr; pr.t = text.p; pr.b = 0;
+		InBucket pr; pr.t = text.p; pr.len = len; pr.b = 0;
 		cub::DeviceSelect::If(nullptr, tb, cit, pos.p, (unsigned long long*)scal.p, (int)(1 << 30), pr); tmp_bytes = std::max(tmp_bytes, tb);
 		cub::CountingInputIterator<uint32_t> c32(0);
 		cub::DeviceSelect::Flagged(nullptr, tb, c32, tied.p, idx.p, (unsigned long long*)scal.p, (int)cap); tmp_bytes = std::max(tmp_bytes, tb);
@@ -510,8 +523,7 @@ extern "C" int cfb_build_index(const cfb_build_opts* o) {
 	bool round_ws = false;       // refinement buffers are allocated on first use (sized by the first tie count)
 	uint32_t round_cap = 0;
 
-	uint64_t row0 = 1;           // row 0 is the empty suffix
-	// row 0: BWT base = last base of the text, sample/ftab handled below
+	uint64_t row0 = 0;           // the empty suffix is the LAST row (row len): '$' sorts after every base
 	int max_rounds = 0;
 	for(int b = 0; b < 16; b++) {
 		const uint32_t n = (uint32_t)hist[b];
@@ -521,7 +533,7 @@ extern "C" int cfb_build_index(const cfb_build_opts* o) {
 		for(uint64_t c0 = 0; c0 < len; c0 += (1ull << 30)) {
 			const uint64_t cn = std::min<uint64_t>(1ull << 30, len - c0);
 			cub::CountingInputIterator<uint64_t> cit(c0);
-			InBucket pr; pr.t = text.p; pr.b = b;
+			InBucket pr; pr.t = text.p; pr.len = len; pr.b = b;
 			size_t tbb = tmp_bytes;
 			BCK(cub::DeviceSelect::If(tmp.p, tbb, cit, pos.p + got, (unsigned long long*)(scal.p + 18), (int)cn, pr));
 			unsigned long long k = 0; BCK(cudaMemcpy(&k, scal.p + 18, 8, cudaMemcpyDeviceToHost));
@@ -591,10 +603,9 @@ extern "C" int cfb_build_index(const cfb_build_opts* o) {
 		row0 += n;
 		if(o->verbose) fprintf(stderr, "[cfb-build] bucket %d: %u suffixes, %d refinement rounds\n", b, n, rounds);
 	}
-	if(row0 != bwt_len) return bfail(CFB_ECUDA, "internal: emitted %llu of %llu rows", (unsigned long long)row0, (unsigned long long)bwt_len);
+	if(row0 != len) return bfail(CFB_ECUDA, "internal: emitted %llu of %llu rows", (unsigned long long)row0, (unsigned long long)len);
 
-	// ---- row 0 (empty suffix, saElt == len): BWT base = text[len-1]; sample = seq of text position len-1
-	std::vector<uint64_t> tail_words(4);
+	// ---- last row (empty suffix, saElt == len): BWT base = text[len-1]; sample = seq of text position len-1
 	uint8_t tail[64]; const uint64_t tail_n = std::min<uint64_t>(len, 40);
 	{
 		std::vector<uint64_t> tw((tail_n + 31) / 32 + 2);
@@ -604,9 +615,8 @@ extern "C" int cfb_build_index(const cfb_build_opts* o) {
 	}
 	{
 		const uint32_t c = tail[tail_n - 1];
-		uint32_t w0 = 0; BCK(cudaMemcpy(&w0, bwt.p, 4, cudaMemcpyDeviceToHost)); w0 |= c; BCK(cudaMemcpy(bwt.p, &w0, 4, cudaMemcpyHostToDevice));
-		// tidx of len-1: last fragment's sequence
-		const uint32_t s0 = m.frag_seq.back(); BCK(cudaMemcpy(sample.p, &s0, 4, cudaMemcpyHostToDevice));
+		uint32_t wv = 0; BCK(cudaMemcpy(&wv, bwt.p + (len >> 4), 4, cudaMemcpyDeviceToHost)); wv |= c << (2 * (len & 15)); BCK(cudaMemcpy(bwt.p + (len >> 4), &wv, 4, cudaMemcpyHostToDevice));
+		if((len & ((1ull << o->off_rate) - 1)) == 0) { const uint32_t s0 = m.frag_seq.back(); BCK(cudaMemcpy(sample.p + (len >> o->off_rate), &s0, 4, cudaMemcpyHostToDevice)); }
 	}
 
 	// ---- sides: per-side counts -> exclusive occ, '$' not counted as A
@@ -632,21 +642,22 @@ extern "C" int cfb_build_index(const cfb_build_opts* o) {
 	{ std::vector<unsigned long long> fc(ftab_len + 1); BCK(cudaMemcpy(fc.data(), ftab_cnt.p, (ftab_len + 1) * 8, cudaMemcpyDeviceToHost)); for(uint64_t i = 0; i < ftab_len; i++) ftab[i] = fc[i]; }
 	std::vector<uint8_t> absorb(ftab_len, 0);
 	{
-		// suffixes shorter than ftabChars, in suffix order: (padded prefix, length)
+		// suffixes shorter than ftabChars sort after every longer suffix sharing their bases: the next long
+		// suffix in order is the first one whose prefix exceeds the short suffix padded with T's
 		const int fc = o->ftab_chars;
-		std::vector<std::pair<uint64_t, int> > shorts;
+		std::vector<std::pair<uint64_t, int> > shorts;       // (first prefix value strictly after the suffix, -length)
 		for(int L = 0; L < fc && (uint64_t)L <= len; L++) {
 			uint64_t v = 0; for(int k = 0; k < L; k++) v = (v << 2) | tail[tail_n - L + k];
-			shorts.push_back(std::make_pair(v << (2 * (fc - L)), L));
+			const int padb = 2 * (fc - L);
+			const uint64_t after = ((v << padb) | ((1ull << padb) - 1)) + 1;
+			shorts.push_back(std::make_pair(after, -L));
 		}
 		std::sort(shorts.begin(), shorts.end());
-		// occupied prefixes: ftab[x+1] > 0
 		size_t i = 0;
 		while(i < shorts.size()) {
-			uint64_t x = shorts[i].first;
-			while(x + 1 < ftab_len && ftab[x + 1] == 0) x++;        // next long suffix in order
+			uint64_t x = shorts[i].first;                        // candidate sufInt of the next long suffix
+			while(x + 1 < ftab_len && ftab[x + 1] == 0) x++;
 			size_t j = i; uint8_t cntv = 0;
-			// all consecutive short suffixes whose next long suffix is the same one
 			while(j < shorts.size()) {
 				uint64_t y = shorts[j].first; while(y + 1 < ftab_len && ftab[y + 1] == 0) y++;
 				if(y != x) break;
@@ -709,7 +720,6 @@ extern "C" int cfb_build_index(const cfb_build_opts* o) {
 			const size_t k = std::lower_bound(m.mark_pos.begin(), m.mark_pos.end(), bp[i]) - m.mark_pos.begin();
 			bm[br[i]] = m.mark_idx[k];
 		}
-		// the empty suffix (row 0, saElt == len) is tested against the mark bitmap as well; len is never marked
 		FILE* f = fopen((base + ".4.cf").c_str(), "wb");
 		if(!f) return bfail(CFB_EIO, "could not open %s.4.cf for writing", base.c_str());
 		put<int32_t>(f, 1); put<uint64_t>(f, bm.size());

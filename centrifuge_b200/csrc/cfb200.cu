@@ -33,29 +33,175 @@ struct SearchArgs {
 	unsigned int* task_ctr; uint32_t ntasks, chunk;
 	unsigned int* overflow;
 	Counters* ctr;
+	const uint64_t* pk; const uint32_t* nm; uint32_t W;   // packed reads (k_pack)
 };
 
-template <bool COUNT>
+// row -> (side, offset in side).  Rows are < 2^39 for any index that fits in HBM, so row>>7 fits
+// 32 bits and the division by 3 is a single mul.hi (384 = 128 * 3).
+__device__ __forceinline__ void row_locus(uint64_t row, uint64_t& side, uint32_t& off) {
+	const uint32_t q = (uint32_t)(row >> 7) / 3u;
+	side = q; off = (uint32_t)(row - (uint64_t)q * 384u);
+}
+__device__ __forceinline__ uint64_t shl64(uint64_t v, uint32_t n) {   // PTX shl clamps n >= 64 to "all shifted out"
+	uint64_t r; asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(n)); return r;
+}
+__device__ __forceinline__ uint64_t shr64(uint64_t v, uint32_t n) {
+	uint64_t r; asm("shr.b64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(n)); return r;
+}
+
+// =======================================================================================
+// k_pack: reads -> 2-bit words in *consumption order* of the backward search, both strands.
+// Position p of a packed strand is the base the search looks at when dep == p:
+//   strand 0 (fw): fw[rlen-1-p]      strand 1 (rc): comp(fw[p])      (Read::constructRevComps)
+// base p sits in bits 2*(p&31) of word p>>5; N -> code 0 plus a bit in the parallel N mask.
+// =======================================================================================
+struct PackArgs { BatchView b; uint64_t* pk; uint32_t* nm; uint32_t W; };
+
+__global__ void __launch_bounds__(128) k_pack(const PackArgs a) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (task, word)
+	const uint64_t ntasks = (uint64_t)a.b.n_units * a.b.n_mates * 2;
+	if(i >= ntasks * a.W) return;
+	const uint64_t t = i / a.W; const uint32_t k = (uint32_t)(i - t * a.W);
+	const uint32_t per = 2u * (uint32_t)a.b.n_mates;
+	const uint32_t unit = (uint32_t)(t / per), rem = (uint32_t)(t - (uint64_t)unit * per);
+	const int mate = (int)(rem >> 1), strand = (int)(rem & 1);
+	const uint32_t len = a.b.len[mate][unit];
+	const uint8_t* fw = a.b.bases + a.b.off[mate][unit];
+	uint64_t w = 0; uint32_t n = 0;
+	for(uint32_t q = 0; q < 32; q++) {
+		const uint32_t p = k * 32 + q;
+		if(p >= len) break;
+		int c = strand == 0 ? fw[len - 1 - p] : fw[p];
+		if(c > 3) { n |= 1u << q; c = 0; } else if(strand) c = 3 - c;
+		w |= (uint64_t)c << (2 * q);
+	}
+	a.pk[i] = w; a.nm[i] = n;
+}
+
+// G lanes own one walk; lane gl holds the NL = 8/G 16-byte pieces q = gl*NL + j of a 128-byte side
+// (q < 6: 64 BWT bases each, q = 6: occ[A],occ[C], q = 7: occ[G],occ[T]).
+template <int G> struct Side { uint4 d[8 / G]; };
+
+template <int G>
+__device__ __forceinline__ void side_load(Side<G>& r, const uint4* sides4, uint64_t s, unsigned gl, uint32_t need_bases, int c) {
+	constexpr int NL = 8 / G;
+	const uint4* p = sides4 + s * 8 + gl * NL;
+	#pragma unroll
+	for(int j = 0; j < NL; j++) {
+		const int q = (int)gl * NL + j;
+		// only the sectors the rank needs: BWT pieces below `need_bases`, and the occ pair of base c
+		const bool want = q < 6 ? ((uint32_t)(64 * q) < need_bases) : (q == 6 + (c >> 1));
+		r.d[j] = want ? __ldg(p + j) : make_uint4(0, 0, 0, 0);
+	}
+}
+// match mask of one 16-byte piece as two u64 (bit 2i set <=> base i == c)
+__device__ __forceinline__ void piece_match(const uint4& d, uint64_t rep, uint64_t& m0, uint64_t& m1) {
+	const uint64_t v0 = (uint64_t)d.x | ((uint64_t)d.y << 32), v1 = (uint64_t)d.z | ((uint64_t)d.w << 32);
+	const uint64_t x0 = ~(v0 ^ rep), x1 = ~(v1 ^ rep);
+	m0 = x0 & (x0 >> 1) & 0x5555555555555555ull; m1 = x1 & (x1 >> 1) & 0x5555555555555555ull;
+}
+// number of set match bits among the first n (0..64) bases of a piece
+__device__ __forceinline__ uint32_t piece_prefix(uint64_t m0, uint64_t m1, int n) {
+	const int n0 = n < 32 ? n : 32, n1 = n - 32;            // n1 may be negative
+	uint32_t r = __popcll(shl64(m0, (uint32_t)(64 - 2 * n0)));
+	if(n1 > 0) r += __popcll(shl64(m1, (uint32_t)(64 - 2 * n1)));
+	return r;
+}
+// rank of base c below offT and offB in the same side; returns cT | cB << 16 (this lane's share)
+template <int G>
+__device__ __forceinline__ uint32_t side_count2(const Side<G>& r, unsigned gl, uint64_t rep, uint32_t offT, uint32_t offB) {
+	constexpr int NL = 8 / G;
+	uint32_t acc = 0;
+	#pragma unroll
+	for(int j = 0; j < NL; j++) {
+		const int q = (int)gl * NL + j;
+		if(q < 6) {
+			uint64_t m0, m1; piece_match(r.d[j], rep, m0, m1);
+			int kT = (int)offT - 64 * q; kT = kT < 0 ? 0 : (kT > 64 ? 64 : kT);
+			int kB = (int)offB - 64 * q; kB = kB < 0 ? 0 : (kB > 64 ? 64 : kB);
+			acc += piece_prefix(m0, m1, kT) | (piece_prefix(m0, m1, kB) << 16);
+		}
+	}
+	return acc;
+}
+template <int G>
+__device__ __forceinline__ uint32_t side_count1(const Side<G>& r, unsigned gl, uint64_t rep, uint32_t off) {
+	constexpr int NL = 8 / G;
+	uint32_t acc = 0;
+	#pragma unroll
+	for(int j = 0; j < NL; j++) {
+		const int q = (int)gl * NL + j;
+		if(q < 6) {
+			uint64_t m0, m1; piece_match(r.d[j], rep, m0, m1);
+			int k = (int)off - 64 * q; k = k < 0 ? 0 : (k > 64 ? 64 : k);
+			acc += piece_prefix(m0, m1, k);
+		}
+	}
+	return acc;
+}
+template <int G>
+__device__ __forceinline__ uint32_t gsum(uint32_t x, unsigned gmask) {
+	#pragma unroll
+	for(int o = 1; o < G; o <<= 1) x += __shfl_xor_sync(gmask, x, o);
+	return x;
+}
+template <int G>
+__device__ __forceinline__ uint64_t side_occ(const Side<G>& r, int c, unsigned gmask, unsigned gbase) {
+	constexpr int NL = 8 / G;
+	const int q = 6 + (c >> 1), j = q % NL;
+	uint4 v = r.d[NL - 1];
+	#pragma unroll
+	for(int jj = 0; jj < NL - 1; jj++) if(jj == j) v = r.d[jj];
+	uint32_t lo = (c & 1) ? v.z : v.x, hi = (c & 1) ? v.w : v.y;
+	if(G > 1) { const int src = gbase + q / NL; lo = __shfl_sync(gmask, lo, src); hi = __shfl_sync(gmask, hi, src); }
+	return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+template <int G>
+__device__ __forceinline__ int side_char(const Side<G>& r, uint32_t off, unsigned gmask, unsigned gbase) {
+	constexpr int NL = 8 / G;
+	const int q = (int)(off >> 6), j = q % NL;
+	uint4 v = r.d[0];
+	#pragma unroll
+	for(int jj = 1; jj < NL; jj++) if(jj == j) v = r.d[jj];
+	const uint32_t w = sel_word(v, (off >> 4) & 3);
+	uint32_t ch = (w >> ((off & 15) * 2)) & 3;
+	if(G > 1) ch = __shfl_sync(gmask, ch, gbase + q / NL);
+	return (int)ch;
+}
+
+struct Walk2 {           // group-uniform state of one greedy strand walk over a packed read
+	const uint64_t* pk; const uint32_t* nm;   // packed strand of the current task
+	uint32_t rlen, tid, cur, dep, offset, nh, tnext, tend;
+	uint64_t top, bot, fi;
+	uint64_t rw0, rw1; uint32_t nw0, nw1, rwi;   // packed words rwi, rwi+1 and their N masks
+	int mode;
+};
+
+template <bool COUNT, int G>
 struct SearchCtx {
 	const SearchArgs& a; unsigned gmask, gbase, gl;
 	unsigned long long c_ps, c_ft, c_sides, c_lf;
 	__device__ __forceinline__ SearchCtx(const SearchArgs& a_) : a(a_), c_ps(0), c_ft(0), c_sides(0), c_lf(0) {
 		const unsigned lane = threadIdx.x & 31;
-		gl = lane & 7; gbase = lane & 24; gmask = 0xFFu << gbase;
+		gl = lane & (G - 1); gbase = lane - gl; gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
 	}
-	__device__ __forceinline__ void emit(Walk& w, uint64_t top, uint64_t bot, uint32_t off, uint32_t len) {
+	__device__ __forceinline__ void emit(Walk2& w, uint64_t top, uint64_t bot, uint32_t off, uint32_t len) {
 		if(w.nh < a.cap) {
 			if(gl == 0) { HitRec* h = a.hits + (size_t)w.tid * a.cap + w.nh; h->top = top; h->bot = bot; h->bwoff = off; h->len = len; }
 		} else if(gl == 0) atomicExch(a.overflow, 1u);
 		w.nh++;
 	}
-	// pick the next task of this group (or M_DONE); sets fw/rlen/strand/tid and cur = 0
-	__device__ __forceinline__ bool next_task(Walk& w) {
+	__device__ __forceinline__ void load_words(Walk2& w, uint32_t wi) {
+		w.rw0 = __ldg(w.pk + wi); w.rw1 = __ldg(w.pk + wi + 1);
+		w.nw0 = __ldg(w.nm + wi); w.nw1 = __ldg(w.nm + wi + 1);
+		w.rwi = wi;
+	}
+	__device__ __forceinline__ bool next_task(Walk2& w) {
 		for(;;) {
 			if(w.tnext >= w.tend) {
 				unsigned base = 0;
 				if(gl == 0) base = atomicAdd(a.task_ctr, a.chunk);
-				base = __shfl_sync(gmask, base, gbase);
+				if(G > 1) base = __shfl_sync(gmask, base, gbase);
 				if(base >= a.ntasks) { w.mode = M_DONE; return false; }
 				w.tnext = base; w.tend = min(base + a.chunk, a.ntasks);
 			}
@@ -63,20 +209,19 @@ struct SearchCtx {
 			const uint32_t per = 2u * (uint32_t)a.b.n_mates;
 			const uint32_t unit = w.tid / per, rem = w.tid - unit * per;
 			const int mate = (int)(rem >> 1);
-			w.strand = (int)(rem & 1);
 			const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
 			w.nh = 0;
 			w.rlen = a.b.len[mate][unit];
 			if(!((fl >> mate) & 1) || w.rlen == 0) { if(gl == 0) a.nhits[w.tid] = 0; continue; }
-			w.fw = a.b.bases + a.b.off[mate][unit];
+			w.pk = a.pk + (size_t)w.tid * a.W; w.nm = a.nm + (size_t)w.tid * a.W;
 			w.cur = 0;
 			return true;
 		}
 	}
-	__device__ __forceinline__ void finish_task(Walk& w) { if(gl == 0) a.nhits[w.tid] = w.nh; }
+	__device__ __forceinline__ void finish_task(Walk2& w) { if(gl == 0) a.nhits[w.tid] = w.nh; }
 
 	// Starts partial searches at w.cur until one needs the ftab (mode M_FTAB) or work runs out.
-	__device__ __forceinline__ void start_search(Walk& w) {
+	__device__ __forceinline__ void start_search(Walk2& w) {
 		const uint32_t fc = (uint32_t)a.v.ftab_chars;
 		for(;;) {
 			if(COUNT) c_ps++;
@@ -88,25 +233,24 @@ struct SearchCtx {
 				if(!next_task(w)) return;
 				continue;
 			}
-			uint64_t fi = 0; int bad = -1;
-			for(uint32_t i = 0; i < fc; i++) {            // chars rlen-cur-1-i, i.e. right to left
-				const int c = seq_at(w.fw, w.rlen, w.strand, w.rlen - w.cur - 1 - i);
-				if(c > 3) { bad = (int)i; break; }
-				fi |= (uint64_t)c << (2 * i);             // leftmost base ends up most significant
-			}
-			if(bad >= 0) {                                // hi_aligner.h:951-966
-				const uint32_t hl = (uint32_t)bad + 1;
+			load_words(w, w.cur >> 5);
+			const uint32_t sh = w.cur & 31;
+			const uint64_t win = shr64(w.rw0, 2 * sh) | shl64(w.rw1, 64 - 2 * sh);      // bases cur.., base cur in the low bits
+			const uint32_t nwin = (uint32_t)(((uint64_t)w.nw0 | ((uint64_t)w.nw1 << 32)) >> sh);
+			const uint32_t nbits = nwin & ((1u << fc) - 1u);
+			if(nbits) {                                   // N within the next fc bases, hi_aligner.h:951-966
+				const uint32_t hl = (uint32_t)__ffs(nbits);  // index of the first N + 1
 				w.cur += hl;
 				emit(w, kOff, kOff, w.offset, hl);
 				if(after_hit(w, hl)) continue; else return;
 			}
-			w.fi = fi; w.mode = M_FTAB;
+			w.fi = win & ((1ull << (2 * fc)) - 1ull);     // base cur (rightmost of the 10-mer) least significant
+			w.mode = M_FTAB;
 			return;
 		}
 	}
-	// searchForwardAndReverse restart policy (classifier.h:686-766).  Returns true if another
-	// partial search must start at w.cur on the same or a new task, false if the group is done.
-	__device__ __forceinline__ bool after_hit(Walk& w, uint32_t hlen) {
+	// searchForwardAndReverse restart policy (classifier.h:686-766).
+	__device__ __forceinline__ bool after_hit(Walk2& w, uint32_t hlen) {
 		bool done = w.cur >= w.rlen;
 		if(!done) {
 			if(hlen > a.p.increment) w.cur += 1;
@@ -115,7 +259,7 @@ struct SearchCtx {
 		if(done) { finish_task(w); if(!next_task(w)) return false; }
 		return true;
 	}
-	__device__ __forceinline__ void hit_and_restart(Walk& w) {
+	__device__ __forceinline__ void hit_and_restart(Walk2& w) {
 		const uint32_t hl = w.dep - w.offset;
 		emit(w, w.top, w.bot, w.offset, hl);
 		w.cur = w.dep;
@@ -123,43 +267,46 @@ struct SearchCtx {
 	}
 };
 
-template <bool COUNT>
+template <bool COUNT, int G>
 __global__ void __launch_bounds__(kSearchThreads) k_search(const SearchArgs a) {
-	SearchCtx<COUNT> cx(a);
+	SearchCtx<COUNT, G> cx(a);
 	const unsigned gl = cx.gl, gmask = cx.gmask, gbase = cx.gbase;
 	const uint4* sides4 = reinterpret_cast<const uint4*>(a.v.sides);
-	const uint4* ftab4 = reinterpret_cast<const uint4*>(a.v.ftab);
-	Walk w; w.tnext = w.tend = 0; w.mode = M_DONE; w.nh = 0; w.tid = 0; w.rlen = 0; w.cur = 0; w.dep = 0; w.offset = 0; w.top = w.bot = w.fi = 0; w.strand = 0; w.fw = nullptr;
+	Walk2 w; memset(&w, 0, sizeof w); w.mode = M_DONE;
 	if(cx.next_task(w)) cx.start_search(w);
 
 	while(__any_sync(0xffffffffu, w.mode != M_DONE)) {
 		// ---------------- single fetch point ----------------
-		const uint4* pa = nullptr; const uint4* pb = nullptr;
 		uint32_t offT = 0, offB = 0; uint64_t sT = 0, sB = 0; bool range = false, same = true;
-		int c = 0;
+		int c = 4;
+		uint64_t e0 = 0, e1 = 0;
+		Side<G> da, db;
 		if(w.mode == M_FTAB) {
-			if(gl < 2) pa = ftab4 + ((w.fi + gl) >> 1);
+			if(G == 1) { e0 = __ldg(a.v.ftab + w.fi); e1 = __ldg(a.v.ftab + w.fi + 1); }
+			else if(gl < 2) e0 = __ldg(a.v.ftab + w.fi + gl);
 		} else if(w.mode == M_LF) {
-			sT = w.top / 384; offT = (uint32_t)(w.top - sT * 384);
-			pa = sides4 + sT * 8 + gl;
-			const uint64_t spread = w.bot - w.top;
-			range = spread != 1;
-			sB = sT; offB = offT;
-			if(range) {
-				same = spread < (uint64_t)(384 - offT);   // initFromTopBot bt2_idx.h:326-349
-				if(same) offB = offT + (uint32_t)spread;
-				else { sB = w.bot / 384; offB = (uint32_t)(w.bot - sB * 384); pb = sides4 + sB * 8 + gl; }
+			const uint32_t wi = w.dep >> 5;
+			if(wi != w.rwi && wi != w.rwi + 1) cx.load_words(w, wi);
+			const uint32_t sh = w.dep & 31;
+			const uint64_t rw = wi == w.rwi ? w.rw0 : w.rw1; const uint32_t nw = wi == w.rwi ? w.nw0 : w.nw1;
+			c = ((nw >> sh) & 1u) ? 4 : (int)((rw >> (2 * sh)) & 3);
+			if(c <= 3) {
+				row_locus(w.top, sT, offT);
+				const uint64_t spread = w.bot - w.top;
+				range = spread != 1;
+				sB = sT; offB = offT;
+				if(range) {
+					same = spread < (uint64_t)(384 - offT);   // initFromTopBot bt2_idx.h:326-349
+					if(same) offB = offT + (uint32_t)spread; else row_locus(w.bot, sB, offB);
+				}
+				// rank needs bases [0, off); mapLF1 additionally needs BWT[offT]
+				side_load<G>(da, sides4, sT, gl, same ? (range ? offB : offT + 1) : offT, c);
+				if(!same) side_load<G>(db, sides4, sB, gl, offB, c);
 			}
-			c = seq_at(w.fw, w.rlen, w.strand, w.rlen - w.dep - 1);
 		}
-		uint4 da = make_uint4(0, 0, 0, 0), db = make_uint4(0, 0, 0, 0);
-		if(pa) da = __ldg(pa);
-		if(pb) db = __ldg(pb);
 		// ---------------- consume ----------------
 		if(w.mode == M_FTAB) {
-			const uint64_t lo = (uint64_t)da.x | ((uint64_t)da.y << 32), hi = (uint64_t)da.z | ((uint64_t)da.w << 32);
-			const uint64_t mine = ((w.fi + gl) & 1) ? hi : lo;
-			const uint64_t e0 = __shfl_sync(gmask, mine, gbase), e1 = __shfl_sync(gmask, mine, gbase + 1);
+			if(G > 1) { const uint64_t mine = e0; e0 = __shfl_sync(gmask, mine, gbase); e1 = __shfl_sync(gmask, mine, gbase + 1); }
 			if(COUNT) cx.c_ft++;
 			w.top = ftab_hi(a.v, e0); w.bot = ftab_lo(a.v, e1);
 			w.dep = w.cur + (uint32_t)a.v.ftab_chars;
@@ -174,15 +321,13 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const SearchArgs a) {
 			bool fail = c > 3;
 			uint64_t t = 0, b = 0;
 			if(!fail) {
-				const uint32_t rep = (uint32_t)c * 0x55555555u;
-				const uint4& dsel = same ? da : db;
-				int nT = (int)offT - 64 * (int)gl; int nB = (int)offB - 64 * (int)gl;
-				uint32_t cT = 0, cB = 0;
-				if(gl < 6) { cT = lane_count(da, rep, nT < 0 ? 0 : (nT > 64 ? 64 : nT)); cB = lane_count(dsel, rep, nB < 0 ? 0 : (nB > 64 ? 64 : nB)); }
-				const uint32_t packed = group_sum(cT | (cB << 16), gmask);
-				const uint64_t occT = group_occ(da, c, gmask, gbase);
-				const uint64_t occB = group_occ(dsel, c, gmask, gbase);
-				const int rowc = group_char(da, offT, gmask, gbase);
+				const uint64_t rep = (uint64_t)c * 0x5555555555555555ull;
+				uint32_t packed;
+				if(same) packed = side_count2<G>(da, gl, rep, offT, offB);
+				else packed = side_count1<G>(da, gl, rep, offT) | (side_count1<G>(db, gl, rep, offB) << 16);
+				packed = gsum<G>(packed, gmask);
+				const uint64_t occT = side_occ<G>(da, c, gmask, gbase);
+				const uint64_t occB = same ? occT : side_occ<G>(db, c, gmask, gbase);
 				uint64_t rT = packed & 0xFFFFu, rB = packed >> 16;
 				if(c == 0) {
 					if(sT == a.v.zside && a.v.zoffc < offT) rT--;
@@ -194,6 +339,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const SearchArgs a) {
 					if(COUNT) { cx.c_lf += 2; cx.c_sides += same ? 1 : 2; }
 				} else {                                  // mapLF1 bt2_idx.h:2910-2933
 					if(COUNT) { cx.c_lf += 1; cx.c_sides += 1; }
+					const int rowc = side_char<G>(da, offT, gmask, gbase);
 					if(rowc != c || w.top == a.v.zoff) fail = true;
 					b = t + 1;
 				}
@@ -209,6 +355,16 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const SearchArgs a) {
 	if(COUNT && gl == 0 && a.ctr) {
 		atomicAdd(&a.ctr->partial_searches, cx.c_ps); atomicAdd(&a.ctr->ftab_probes, cx.c_ft);
 		atomicAdd(&a.ctr->sides_search, cx.c_sides); atomicAdd(&a.ctr->lf_steps, cx.c_lf);
+	}
+}
+
+typedef void (*SearchKernel)(const SearchArgs);
+static SearchKernel search_kernel(int g, bool count) {
+	switch(g) {
+		case 1: return count ? k_search<true, 1> : k_search<false, 1>;
+		case 2: return count ? k_search<true, 2> : k_search<false, 2>;
+		case 4: return count ? k_search<true, 4> : k_search<false, 4>;
+		default: return count ? k_search<true, 8> : k_search<false, 8>;
 	}
 }
 
@@ -596,6 +752,7 @@ struct Slot {
 	HBuf<uint8_t> h_bases; HBuf<uint64_t> h_off; HBuf<uint32_t> h_len; HBuf<uint8_t> h_flags;
 	DBuf<uint8_t> d_bases; DBuf<uint64_t> d_off; DBuf<uint32_t> d_len; DBuf<uint8_t> d_flags;
 	// work
+	DBuf<uint64_t> pk; DBuf<uint32_t> nm;
 	DBuf<HitRec> hits; DBuf<uint32_t> nhits; DBuf<uint32_t> nrows; DBuf<uint64_t> row_off; DBuf<uint64_t> bsum;
 	DBuf<uint64_t> rows; DBuf<uint32_t> ids; DBuf<Entry> entries; DBuf<TaxCnt> tcs; DBuf<OutRec> sparse;
 	DBuf<uint32_t> nout; DBuf<uint64_t> out_off; DBuf<OutRec> dense; DBuf<uint32_t> rec_off32;
@@ -607,7 +764,7 @@ struct Slot {
 	bool pending = false;
 	void release() {
 		h_bases.release(); h_off.release(); h_len.release(); h_flags.release(); d_bases.release(); d_off.release(); d_len.release(); d_flags.release();
-		hits.release(); nhits.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
+		pk.release(); nm.release(); hits.release(); nhits.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
 		sparse.release(); nout.release(); out_off.release(); dense.release(); rec_off32.release(); scal.release(); h_scal.release(); h_recs.release(); h_rec_off.release();
 		for(int i = 0; i < 6; i++) if(ev[i]) cudaEventDestroy(ev[i]);
 		if(st) cudaStreamDestroy(st);
@@ -623,7 +780,7 @@ struct cfb_ctx {
 	Slot slots[kSlots];
 	Counters* d_ctr = nullptr; bool count = false;
 	uint64_t launches = 0;
-	int search_blocks = 0, resolve_blocks = 0;
+	int search_blocks = 0, resolve_blocks = 0, group = 8;
 	cfb_dbatch resident; bool resident_used = false;
 };
 
@@ -689,7 +846,8 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 	}
 	CKC(cudaMalloc((void**)&c->d_ctr, sizeof(Counters))); CKC(cudaMemset(c->d_ctr, 0, sizeof(Counters)));
 	int occ = 0;
-	CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<false>, kSearchThreads, 0));
+	{ const char* g = getenv("CFB_GROUP"); if(g) { const int v = atoi(g); if(v == 1 || v == 2 || v == 4 || v == 8) c->group = v; } }
+	CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel(c->group, false), kSearchThreads, 0));
 	c->search_blocks = ix->sm_count * std::max(occ, 1);
 	CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
 	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
@@ -740,7 +898,9 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	if(n == 0) return CFB_OK;
 	if(stage == 0) {
 		if(s.cap == 0) s.cap = s.maxlen / 4 + 8;      // >= #Ns allowed by the N filter (0.15 len) + len/10 + slack
-		CK(s.hits.ensure(ntasks * s.cap)); CK(s.nhits.ensure(ntasks)); CK(s.nrows.ensure(n)); CK(s.row_off.ensure(n + 1));
+		CK(s.hits.ensure(ntasks * s.cap)); CK(s.nhits.ensure(ntasks));
+		const uint32_t W = (s.maxlen + 31) / 32 + 1;
+		CK(s.pk.ensure(ntasks * W + 2)); CK(s.nm.ensure(ntasks * W + 2)); CK(s.nrows.ensure(n)); CK(s.row_off.ensure(n + 1));
 		CK(s.bsum.ensure(scan_blocks + 1)); CK(s.nout.ensure(n)); CK(s.out_off.ensure(n + 1)); CK(s.rec_off32.ensure(n + 1));
 		s.rows_cap = std::max<uint64_t>(s.rows_cap, std::max<uint64_t>(n * 12, 4096));
 	}
@@ -756,11 +916,16 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	ua.overflow = (unsigned int*)(s.scal.p + 2); ua.ctr = ctr;
 	if(stage == 0) {
 		SearchArgs sa; sa.v = c->view; sa.p = c->prm; sa.b = s.bv; sa.hits = s.hits.p; sa.nhits = s.nhits.p; sa.cap = s.cap;
+		const uint32_t W = (s.maxlen + 31) / 32 + 1;
+		sa.pk = s.pk.p; sa.nm = s.nm.p; sa.W = W;
+		{ PackArgs pa; pa.b = s.bv; pa.pk = s.pk.p; pa.nm = s.nm.p; pa.W = W;
+		  k_pack<<<(unsigned)((ntasks * W + 127) / 128), 128, 0, s.st>>>(pa); c->launches++; }
 		sa.task_ctr = (unsigned int*)(s.scal.p + 0); sa.ntasks = (uint32_t)ntasks; sa.overflow = (unsigned int*)(s.scal.p + 2); sa.ctr = ctr;
-		const uint64_t groups = (uint64_t)c->search_blocks * (kSearchThreads / kGroup);
+		const uint64_t per_block = kSearchThreads / c->group;
+		const uint64_t groups = (uint64_t)c->search_blocks * per_block;
 		uint64_t chunk = ntasks / (groups * 8); sa.chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(chunk, 1), 16);
-		const int blocks = (int)std::min<uint64_t>((uint64_t)c->search_blocks, (ntasks + kSearchThreads / kGroup - 1) / (kSearchThreads / kGroup));
-		if(c->count) k_search<true><<<blocks, kSearchThreads, 0, s.st>>>(sa); else k_search<false><<<blocks, kSearchThreads, 0, s.st>>>(sa);
+		const int blocks = (int)std::min<uint64_t>((uint64_t)c->search_blocks, (ntasks + per_block - 1) / per_block);
+		search_kernel(c->group, c->count)<<<blocks, kSearchThreads, 0, s.st>>>(sa);
 		c->launches++;
 		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
 		k_prep<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
