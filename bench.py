@@ -116,6 +116,40 @@ def ref_reads_per_s(base, fq, threads):
     return time.time() - t0
 
 
+class RefArm:
+    """The unmodified reference binary on the host cores.  Index load is excluded by differencing two
+    sample sizes; the thread count is the best of a short sweep (the reference's one-read-per-mutex
+    input loop, pat.h:786-811, stops scaling well before 128 threads)."""
+
+    def __init__(self, a, base, d, device=0):
+        self.base, self.d = base, d
+        self.n_small, self.n = 20000, a.cpu_sample
+        self.fq_small, self.fq = os.path.join(d, "sample_%d.fq" % self.n_small), os.path.join(d, "sample_%d.fq" % self.n)
+        for n, fq in ((self.n_small, self.fq_small), (self.n, self.fq)):
+            if not os.path.exists(fq):
+                write_fastq(fq, make_reads(a.genera, a.species, a.genome_len, 12345, n, a.rdlen, 999, device))
+        ncores = os.cpu_count() or 1
+        self.load_s = {}
+        best = None
+        for p in sorted(set(min(x, ncores) for x in (8, 16, 24, 32, 64, ncores))):
+            t1 = ref_reads_per_s(base, self.fq_small, p)
+            t2 = ref_reads_per_s(base, self.fq, p)
+            rate = (self.n - self.n_small) / max(t2 - t1, 1e-6)
+            self.load_s[p] = t1
+            log("reference -p %d: %.0f reads/s (%.1f s for %d reads, %.1f s for %d)" % (p, rate, t2, self.n, t1, self.n_small))
+            if best is None or rate > best[1]:
+                best = (p, rate)
+            elif rate < 0.5 * best[1]:
+                break
+        self.threads, self.sweep_rate = best
+
+    def step(self):
+        """seconds of classification work for self.n - self.n_small reads (index load differenced out)"""
+        t2 = ref_reads_per_s(self.base, self.fq, self.threads)
+        t1 = ref_reads_per_s(self.base, self.fq_small, self.threads)
+        return max(t2 - t1, 1e-6), self.n - self.n_small
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -131,7 +165,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cfb200", choices=["cfb200", "reference"])
-    ap.add_argument("--genera", type=int, default=int(os.environ.get("CFB_BENCH_GENERA", 10)))
+    ap.add_argument("--genera", type=int, default=int(os.environ.get("CFB_BENCH_GENERA", 900)))
     ap.add_argument("--species", type=int, default=int(os.environ.get("CFB_BENCH_SPECIES", 10)))
     ap.add_argument("--genome-len", type=int, default=int(os.environ.get("CFB_BENCH_GENOME_LEN", 1000000)))
     ap.add_argument("--reads", type=int, default=int(os.environ.get("CFB_BENCH_READS", 2000000)), help="reads per step per GPU")
@@ -147,20 +181,21 @@ def main():
         if rank != 0:
             return 0
         base, d = get_index(a.genera, a.species, a.genome_len, 12345)
-        n = a.cpu_sample
-        fq = os.path.join(d, "sample_%d.fq" % n)
-        if not os.path.exists(fq):
-            write_fastq(fq, make_reads(a.genera, a.species, a.genome_len, 12345, n, a.rdlen, 999))
+        arm = RefArm(a, base, d)
         for _ in range(min(a.warmup, 1)):
-            ref_reads_per_s(base, fq, ncores)
-        t = [ref_reads_per_s(base, fq, ncores) for _ in range(a.steps)]
-        tot = sum(t)
-        val = n * a.steps / tot
+            arm.step()
+        tot, nreads = 0.0, 0
+        for _ in range(a.steps):
+            t, n = arm.step()
+            tot += t; nreads += n
+        val = nreads / tot
+        sample = "%d reads per step (bounded sample), centrifuge-class -p %d (best of a thread sweep up to %d), FASTQ in, TSV to /dev/null, index load differenced out" % (
+            nreads // a.steps, arm.threads, ncores)
         print(json.dumps({"metric": "reads/sec (100 bp SE classification)", "value": val, "unit": "reads/s", "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": min(a.warmup, 1), "ms_per_step": 1000 * tot / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "u64", "data": "synthetic", "impl": "reference",
-                          "config": {"workload": workload, "sample": "%d reads per step (bounded sample of the workload), FASTQ in, TSV to /dev/null, index load included" % n},
-                          "cpu_baseline": {"value": val, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "%d reads x %d steps, centrifuge-class -p %d" % (n, a.steps, ncores)},
+                          "config": {"workload": workload, "sample": sample},
+                          "cpu_baseline": {"value": val, "unit": "reads/s", "cores": arm.threads, "kind": "reference", "sample": sample},
                           "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -277,7 +312,7 @@ def main():
                    "parallelism": "reads sharded over %d GPU(s), index replicated, 1 NCCL all-reduce of per-taxon counts per step" % world},
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h // max(a.steps, 1))},
         "gpu_launches": int(launches_value),
-        "roofline": {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "k_search_t", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_search), "kernel_ms": 1000 * search_s,
                      "sides_per_read": ctr["sides_search"] / max(ctr["units"], 1), "walk_bytes_per_launch": int(bytes_walk)},
         "kernel_ms": {"search": kms[0] / a.steps, "prep_rows": kms[1] / a.steps, "resolve": kms[2] / a.steps, "score_compact": kms[3] / a.steps, "total": step_ms},
@@ -287,13 +322,10 @@ def main():
     if rank == 0:
         # bounded CPU baseline: the unmodified reference binary on the host cores
         try:
-            ns = a.cpu_sample
-            fq = os.path.join(d, "sample_%d.fq" % ns)
-            if not os.path.exists(fq):
-                write_fastq(fq, make_reads(a.genera, a.species, a.genome_len, 12345, ns, a.rdlen, 999, local))
-            tt = ref_reads_per_s(base, fq, ncores)
-            out["cpu_baseline"] = {"value": ns / tt, "unit": "reads/s", "cores": ncores, "kind": "reference",
-                                   "sample": "%d reads, centrifuge-class -p %d, FASTQ in, TSV to /dev/null, index load included (%.1f s)" % (ns, ncores, tt)}
+            arm = RefArm(a, base, d, local)
+            tt, nn = arm.step()
+            out["cpu_baseline"] = {"value": nn / tt, "unit": "reads/s", "cores": arm.threads, "kind": "reference",
+                                   "sample": "%d reads, centrifuge-class -p %d (best of a sweep up to %d threads), FASTQ in, TSV to /dev/null, index load differenced out" % (nn, arm.threads, ncores)}
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "failed: %s" % e}
         print(json.dumps(out))

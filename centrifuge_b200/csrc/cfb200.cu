@@ -17,7 +17,7 @@ using namespace cfb;
 // =======================================================================================
 // k_search
 // =======================================================================================
-enum { M_DONE = 0, M_FTAB = 1, M_LF = 2 };
+enum { M_DONE = 0, M_FTAB = 1, M_LF = 2, M_NEED = 3 };
 
 struct Walk {            // group-uniform state of one greedy strand walk
 	const uint8_t* fw; uint32_t rlen; int strand; uint32_t tid;
@@ -30,7 +30,7 @@ struct Walk {            // group-uniform state of one greedy strand walk
 struct SearchArgs {
 	IndexView v; Params p; BatchView b;
 	HitRec* hits; uint32_t* nhits; uint32_t cap;
-	unsigned int* task_ctr; uint32_t ntasks, chunk;
+	unsigned int* task_ctr; unsigned long long* task_ctr64; uint32_t ntasks, chunk;
 	unsigned int* overflow;
 	Counters* ctr;
 	const uint64_t* pk; const uint32_t* nm; uint32_t W;   // packed reads (k_pack)
@@ -181,7 +181,8 @@ template <bool COUNT, int G>
 struct SearchCtx {
 	const SearchArgs& a; unsigned gmask, gbase, gl;
 	unsigned long long c_ps, c_ft, c_sides, c_lf;
-	__device__ __forceinline__ SearchCtx(const SearchArgs& a_) : a(a_), c_ps(0), c_ft(0), c_sides(0), c_lf(0) {
+	bool pooled;        // thread-per-walk kernels: tasks are handed out at the loop top (pool_take)
+	__device__ __forceinline__ SearchCtx(const SearchArgs& a_) : a(a_), c_ps(0), c_ft(0), c_sides(0), c_lf(0), pooled(false) {
 		const unsigned lane = threadIdx.x & 31;
 		gl = lane & (G - 1); gbase = lane - gl; gmask = ((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
 	}
@@ -196,7 +197,21 @@ struct SearchCtx {
 		w.nw0 = __ldg(w.nm + wi); w.nw1 = __ldg(w.nm + wi + 1);
 		w.rwi = wi;
 	}
+	// bind walk state to task id w.tid; false if the mate is filtered / empty
+	__device__ __forceinline__ bool bind_task(Walk2& w) {
+		const uint32_t per = 2u * (uint32_t)a.b.n_mates;
+		const uint32_t unit = w.tid / per, rem = w.tid - unit * per;
+		const int mate = (int)(rem >> 1);
+		const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
+		w.nh = 0;
+		w.rlen = a.b.len[mate][unit];
+		if(!((fl >> mate) & 1) || w.rlen == 0) { a.nhits[w.tid] = 0; return false; }
+		w.pk = a.pk + (size_t)w.tid * a.W; w.nm = a.nm + (size_t)w.tid * a.W;
+		w.cur = 0;
+		return true;
+	}
 	__device__ __forceinline__ bool next_task(Walk2& w) {
+		if(pooled) { w.mode = M_NEED; return false; }
 		for(;;) {
 			if(w.tnext >= w.tend) {
 				unsigned base = 0;
@@ -358,10 +373,199 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const SearchArgs a) {
 	}
 }
 
+// ---------------------------------------------------------------------------------------
+// Work distribution for the thread-per-walk kernels: a warp owns a pool [base, end) of task ids
+// refilled with ONE global atomic per `chunk` (>= 32) tasks; lanes that need work take consecutive
+// ids by ballot rank at a convergent point of the loop.  (A per-lane atomicAdd on one address
+// serialises in L2: ~1M same-address atomics cost more than the whole resolve kernel.)
+// ---------------------------------------------------------------------------------------
+struct WarpPool { unsigned long long base, end; };
+__device__ __forceinline__ bool pool_take(WarpPool& P, bool want, unsigned long long* ctr, unsigned long long total, unsigned chunk, unsigned long long& out) {
+	const unsigned need = __ballot_sync(0xffffffffu, want);
+	if(!need) return false;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned cnt = __popc(need), r = __popc(need & ((1u << lane) - 1u));
+	const unsigned long long avail = P.end - P.base;
+	unsigned long long nb = 0;
+	const bool refill = avail < cnt;
+	if(refill) { if(lane == 0) nb = atomicAdd(ctr, (unsigned long long)chunk); nb = __shfl_sync(0xffffffffu, nb, 0); }
+	unsigned long long t, lim;
+	if(r < avail) { t = P.base + r; lim = P.end; }
+	else { t = nb + (r - avail); lim = nb + chunk < total ? nb + chunk : total; }
+	if(refill) { P.base = nb + (cnt - avail); P.end = nb + chunk < total ? nb + chunk : total; if(P.base > P.end) P.base = P.end; }
+	else P.base += cnt;
+	out = t;
+	return want && t < lim;
+}
+
+// ---------------------------------------------------------------------------------------
+// Re-blocked device index.  The `.cf` side (96 B of BWT = 384 rows + 4 x u64 occ) is the unit the
+// reference's CPU code walks; for the GPU each side is split at load time into three 64-byte
+// blocks of 128 rows:  u64 occ[A,C,G,T] counted before the block ('$' excluded) | 4 x u64 of BWT.
+// One LF step then touches half a cache line (two 32-byte sectors), the row -> block map is a shift,
+// and the rank runs over at most 128 bases.  Results are identical to countBt2Side (bt2_idx.h:2192).
+// ---------------------------------------------------------------------------------------
+__global__ void k_build_blocks(const uint64_t* sides, uint64_t num_sides, uint64_t zside, uint32_t zoffc, uint64_t* blocks) {
+	const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(b > num_sides * 3) return;
+	// block num_sides*3 is a sentinel holding the total counts: an exclusive bound bot == len+1 lands
+	// on it when len+1 is a multiple of 384 (then the last side has no padding and the totals are exact)
+	const bool sentinel = b == num_sides * 3;
+	const uint64_t s = sentinel ? num_sides - 1 : b / 3; const uint32_t part = sentinel ? 3u : (uint32_t)(b - s * 3);
+	const uint64_t* sd = sides + s * 16;
+	uint64_t occ[4] = {sd[12], sd[13], sd[14], sd[15]};
+	for(uint32_t k = 0; k < part * 4; k++) {
+		const uint64_t w = sd[k];
+		const uint64_t lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;
+		const uint32_t c1 = __popcll(lo & ~hi), c2 = __popcll(hi & ~lo), c3 = __popcll(hi & lo);
+		occ[1] += c1; occ[2] += c2; occ[3] += c3; occ[0] += 32 - c1 - c2 - c3;
+	}
+	if(s == zside && zoffc < part * 128) occ[0] -= 1;        // the '$' row is stored as A but is not an A
+	uint64_t* o = blocks + b * 8;
+	o[0] = occ[0]; o[1] = occ[1]; o[2] = occ[2]; o[3] = occ[3];
+	for(uint32_t k = 0; k < 4; k++) o[4 + k] = sentinel ? 0ull : sd[part * 4 + k];
+}
+
+struct Blk { uint64_t m[4]; uint32_t pc[4]; };    // match masks of base c and their popcounts
+
+__device__ __forceinline__ void blk_prep(Blk& q, const ulonglong2& a, const ulonglong2& b, uint64_t rep) {
+	const uint64_t w[4] = {a.x, a.y, b.x, b.y};
+	#pragma unroll
+	for(int j = 0; j < 4; j++) {
+		const uint64_t x = ~(w[j] ^ rep);
+		q.m[j] = x & (x >> 1) & 0x5555555555555555ull;
+		q.pc[j] = (uint32_t)__popcll(q.m[j]);
+	}
+}
+// number of matches among the first off (0..127) rows of the block
+__device__ __forceinline__ uint32_t blk_rank(const Blk& q, uint32_t off) {
+	const uint32_t k = off >> 5, part = off & 31;
+	uint32_t r = (k > 0 ? q.pc[0] : 0u) + (k > 1 ? q.pc[1] : 0u) + (k > 2 ? q.pc[2] : 0u);
+	const uint64_t mk = k == 0 ? q.m[0] : (k == 1 ? q.m[1] : (k == 2 ? q.m[2] : q.m[3]));
+	return r + (uint32_t)__popcll(shl64(mk, 64 - 2 * part));
+}
+
+// ---------------------------------------------------------------------------------------
+// k_search_t: one thread per walk.  No cross-lane traffic: each lane reads the 64-byte blocks of its
+// own top and bot rows.  Range and single-row steps share one code path, so the 32 independent walks
+// of a warp diverge only on the restart / ftab paths.
+// ---------------------------------------------------------------------------------------
+template <bool COUNT, int MB>
+__global__ void __launch_bounds__(kSearchThreads, MB) k_search_t(const SearchArgs a) {
+	SearchCtx<COUNT, 1> cx(a);
+	cx.pooled = true;
+	const uint64_t* blocks = a.v.blocks;
+	const uint64_t zblk = a.v.zoff >> 7; const uint32_t zoffb = (uint32_t)(a.v.zoff & 127);
+	Walk2 w; memset(&w, 0, sizeof w); w.mode = M_NEED;
+	WarpPool pool; pool.base = pool.end = 0;
+	bool more = true;      // warp-uniform: the global task counter is not exhausted yet
+
+	for(;;) {
+		// ---------------- hand out tasks (convergent point) ----------------
+		{
+			const bool want = w.mode == M_NEED;
+			if(more) {
+				unsigned long long t = 0;
+				const bool got = pool_take(pool, want, a.task_ctr64, (unsigned long long)a.ntasks, a.chunk, t);
+				if(want) {
+					if(got) { w.tid = (uint32_t)t; if(cx.bind_task(w)) cx.start_search(w); }   // filtered mate: stays M_NEED
+					else w.mode = M_DONE;
+				}
+				if(__any_sync(0xffffffffu, want && !got)) more = false;      // global counter ran past the end
+			} else if(want) w.mode = M_DONE;
+		}
+		if(!__any_sync(0xffffffffu, w.mode != M_DONE)) break;
+		int c = 4;
+		uint64_t e0 = 0, e1 = 0, occT = 0, occB = 0;
+		ulonglong2 t0, t1, b0, b1;
+		t0 = t1 = b0 = b1 = make_ulonglong2(0, 0);
+		const bool lf = w.mode == M_LF;
+		bool range = false, same = true;
+		uint64_t bT = 0, bB = 0; uint32_t oT = 0, oB = 0;
+		if(w.mode == M_FTAB) { e0 = __ldg(a.v.ftab + w.fi); e1 = __ldg(a.v.ftab + w.fi + 1); }
+		else if(lf) {
+			const uint32_t wi = w.dep >> 5;
+			if(wi != w.rwi && wi != w.rwi + 1) cx.load_words(w, wi);
+			const uint32_t sh = w.dep & 31;
+			const uint64_t rw = wi == w.rwi ? w.rw0 : w.rw1; const uint32_t nw = wi == w.rwi ? w.nw0 : w.nw1;
+			c = ((nw >> sh) & 1u) ? 4 : (int)((rw >> (2 * sh)) & 3);
+			if(c <= 3) {
+				range = (w.bot - w.top) != 1;
+				bT = w.top >> 7; oT = (uint32_t)(w.top & 127);
+				bB = w.bot >> 7; oB = (uint32_t)(w.bot & 127);
+				same = !range || bB == bT;
+				const uint64_t* pt = blocks + bT * 8;
+				occT = __ldg(pt + c);
+				t0 = __ldg(reinterpret_cast<const ulonglong2*>(pt + 4)); t1 = __ldg(reinterpret_cast<const ulonglong2*>(pt + 6));
+				if(!same) {
+					const uint64_t* pb = blocks + bB * 8;
+					occB = __ldg(pb + c);
+					b0 = __ldg(reinterpret_cast<const ulonglong2*>(pb + 4)); b1 = __ldg(reinterpret_cast<const ulonglong2*>(pb + 6));
+				}
+			}
+		}
+		if(w.mode == M_FTAB) {
+			if(COUNT) cx.c_ft++;
+			w.top = ftab_hi(a.v, e0); w.bot = ftab_lo(a.v, e1);
+			w.dep = w.cur + (uint32_t)a.v.ftab_chars;
+			if(w.bot <= w.top) {
+				const uint32_t hl = w.dep - w.offset;
+				cx.emit(w, kOff, kOff, w.offset, hl);
+				w.cur = w.dep;
+				if(cx.after_hit(w, hl)) cx.start_search(w);
+			} else if(w.dep < w.rlen) w.mode = M_LF;
+			else cx.hit_and_restart(w);
+		} else if(lf) {
+			bool fail = c > 3;
+			uint64_t t = 0, b = 0;
+			if(!fail) {
+				const uint64_t rep = (uint64_t)c * 0x5555555555555555ull;
+				Blk qT, qB;
+				blk_prep(qT, t0, t1, rep);
+				if(same) { qB = qT; occB = occT; } else blk_prep(qB, b0, b1, rep);
+				uint64_t rT = blk_rank(qT, oT), rB = blk_rank(qB, oB);
+				if(c == 0) {
+					if(bT == zblk && zoffb < oT) rT--;
+					if(bB == zblk && zoffb < oB) rB--;
+				}
+				t = a.v.fchr[c] + occT + rT;
+				b = range ? a.v.fchr[c] + occB + rB : t + 1;
+				if(!range) {                              // mapLF1 bt2_idx.h:2910-2933: BWT[top] must be c
+					const uint32_t k = oT >> 5;
+					const uint64_t wk = k == 0 ? t0.x : (k == 1 ? t0.y : (k == 2 ? t1.x : t1.y));
+					const int rowc = (int)((wk >> (2 * (oT & 31))) & 3);
+					if(rowc != c || w.top == a.v.zoff) fail = true;
+				}
+				if(b <= t) fail = true;
+				if(COUNT) {   // counters keep the reference's side geometry (384 rows per 128-byte side)
+					uint64_t sT; uint32_t offT; row_locus(w.top, sT, offT);
+					const bool same_side = !range || (w.bot - w.top) < (uint64_t)(384 - offT);
+					cx.c_lf += range ? 2 : 1; cx.c_sides += same_side ? 1 : 2;
+				}
+			}
+			if(fail) cx.hit_and_restart(w);
+			else {
+				w.top = t; w.bot = b; w.dep++;
+				if(w.dep >= w.rlen) cx.hit_and_restart(w);
+			}
+		}
+	}
+	if(COUNT && a.ctr) {
+		atomicAdd(&a.ctr->partial_searches, cx.c_ps); atomicAdd(&a.ctr->ftab_probes, cx.c_ft);
+		atomicAdd(&a.ctr->sides_search, cx.c_sides); atomicAdd(&a.ctr->lf_steps, cx.c_lf);
+	}
+}
+
 typedef void (*SearchKernel)(const SearchArgs);
 static SearchKernel search_kernel(int g, bool count) {
 	switch(g) {
-		case 1: return count ? k_search<true, 1> : k_search<false, 1>;
+		case 1: {
+			static int mb = -1;
+			if(mb < 0) { const char* e = getenv("CFB_MINB"); mb = e ? atoi(e) : 5; }
+			if(count) return k_search_t<true, 4>;
+			switch(mb) { case 4: return k_search_t<false, 4>; case 6: return k_search_t<false, 6>; case 8: return k_search_t<false, 8>; default: return k_search_t<false, 5>; }
+		}
+		case 16: return count ? k_search<true, 1> : k_search<false, 1>;   // generic template at G = 1 (A/B only)
 		case 2: return count ? k_search<true, 2> : k_search<false, 2>;
 		case 4: return count ? k_search<true, 4> : k_search<false, 4>;
 		default: return count ? k_search<true, 8> : k_search<false, 8>;
@@ -495,7 +699,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_apply(const uint32_t* in, u
 // =======================================================================================
 // k_resolve : group of 8 lanes per SA row
 // =======================================================================================
-enum { R_DONE = 0, R_WALK = 1, R_SAMPLE = 2 };
+enum { R_DONE = 0, R_WALK = 1, R_SAMPLE = 2, R_NEED = 3 };
 struct ResolveArgs {
 	IndexView v; const uint64_t* rows; uint32_t* ids; const uint64_t* total; uint64_t rows_cap;
 	unsigned long long* task_ctr; uint32_t chunk; Counters* ctr;
@@ -577,6 +781,78 @@ __global__ void __launch_bounds__(kSearchThreads) k_resolve(const ResolveArgs a)
 		}
 	}
 	if(COUNT && gl == 0 && a.ctr) { atomicAdd(&a.ctr->walk_steps, c_walk); atomicAdd(&a.ctr->rows_resolved, c_rows); }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_resolve_t: one thread per SA row over the re-blocked index (same walk as k_resolve).
+// ---------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kSearchThreads, 8) k_resolve_t(const ResolveArgs a) {
+	const uint64_t* blocks = a.v.blocks;
+	const uint64_t zblk = a.v.zoff >> 7; const uint32_t zoffb = (uint32_t)(a.v.zoff & 127);
+	uint64_t n = *a.total; if(n > a.rows_cap) n = a.rows_cap;
+	const uint64_t lowmask = ((uint64_t)1 << a.v.off_rate) - 1;
+	uint64_t idx = 0, row = 0;
+	int mode = R_NEED;
+	unsigned long long c_walk = 0, c_rows = 0;
+	WarpPool pool; pool.base = pool.end = 0;
+	bool more = true;
+	// classify `row` without memory: next mode; a '$' row resolves on the spot
+	auto settle = [&](uint64_t r) -> int {
+		if(r == a.v.zoff) { a.ids[idx] = 0; return R_NEED; }
+		if((r & lowmask) == 0) return R_SAMPLE;
+		return R_WALK;
+	};
+	auto next_row = [&]() { mode = R_NEED; };
+	for(;;) {
+		{
+			const bool want = mode == R_NEED;
+			if(more) {
+				unsigned long long t = 0;
+				const bool got = pool_take(pool, want, a.task_ctr, (unsigned long long)n, a.chunk, t);
+				if(want) {
+					if(got) { idx = t; row = a.rows[idx]; if(COUNT) c_rows++; mode = settle(row); }
+					else mode = R_DONE;
+				}
+				if(__any_sync(0xffffffffu, want && !got)) more = false;
+			} else if(want) mode = R_DONE;
+		}
+		if(!__any_sync(0xffffffffu, mode != R_DONE)) break;
+		ulonglong2 o0, o1, d0, d1; o0 = o1 = d0 = d1 = make_ulonglong2(0, 0);
+		uint32_t bits = 0, samp = 0; bool chk = false;
+		const uint64_t blk = row >> 7; const uint32_t off = (uint32_t)(row & 127);
+		if(mode == R_WALK) {
+			const ulonglong2* p = reinterpret_cast<const ulonglong2*>(blocks + blk * 8);
+			o0 = __ldg(p); o1 = __ldg(p + 1); d0 = __ldg(p + 2); d1 = __ldg(p + 3);
+			chk = a.v.n_boundaries && a.v.last_boundary > 0 && row <= a.v.last_boundary;
+			if(chk) bits = __ldg(a.v.bbits + ((row >> a.v.bshift) >> 5));
+		} else if(mode == R_SAMPLE) {
+			samp = a.v.sample32 ? __ldg(a.v.sample32 + (row >> a.v.off_rate)) : (uint32_t)__ldg(a.v.sample16 + (row >> a.v.off_rate));
+		}
+		if(mode == R_SAMPLE) { a.ids[idx] = samp; next_row(); }
+		else if(mode == R_WALK) {
+			bool found = false;
+			if(chk && ((bits >> ((row >> a.v.bshift) & 31)) & 1u)) {
+				uint32_t lo = 0, hi = a.v.n_boundaries;
+				while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(a.v.brow[mid] < row) lo = mid + 1; else hi = mid; }
+				if(lo < a.v.n_boundaries && a.v.brow[lo] == row) { found = true; a.ids[idx] = a.v.sample32 ? a.v.bseq[lo] : (uint32_t)(uint16_t)a.v.bseq[lo]; }
+			}
+			if(found) next_row();
+			else {
+				const uint32_t k = off >> 5;
+				const uint64_t wk = k == 0 ? d0.x : (k == 1 ? d0.y : (k == 2 ? d1.x : d1.y));
+				const int c = (int)((wk >> (2 * (off & 31))) & 3);
+				const uint64_t occ = c == 0 ? o0.x : (c == 1 ? o0.y : (c == 2 ? o1.x : o1.y));
+				Blk q; blk_prep(q, d0, d1, (uint64_t)c * 0x5555555555555555ull);
+				uint64_t r = blk_rank(q, off);
+				if(c == 0 && blk == zblk && zoffb < off) r--;
+				row = a.v.fchr[c] + occ + r;
+				if(COUNT) c_walk++;
+				mode = settle(row);
+			}
+		}
+	}
+	if(COUNT && a.ctr) { atomicAdd(&a.ctr->walk_steps, c_walk); atomicAdd(&a.ctr->rows_resolved, c_rows); }
 }
 
 // =======================================================================================
@@ -708,6 +984,14 @@ extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out)
 		v.last_boundary = h.last_boundary; v.num_sides = h.num_sides;
 		v.n_boundaries = (uint32_t)h.brow.size(); v.n_seqs = (uint32_t)h.seq_taxid.size();
 		v.off_rate = h.off_rate; v.ftab_chars = h.ftab_chars; v.bshift = h.bshift;
+		{   // re-blocked replica for the thread-per-walk kernels
+			uint64_t* blk = nullptr; const uint64_t nb = h.num_sides * 3;
+			CK(cudaMalloc((void**)&blk, (nb + 1) * 64));
+			ix->dptrs.push_back(blk); ix->device_bytes += (nb + 1) * 64;
+			k_build_blocks<<<(unsigned)((nb + 1 + 255) / 256), 256>>>(v.sides, h.num_sides, v.zside, v.zoffc, blk);
+			CK(cudaDeviceSynchronize());
+			v.blocks = blk; v.num_blocks = nb;
+		}
 		// host copies of the big arrays are no longer needed once uploaded
 		std::vector<uint8_t>().swap(ix->h.sides);
 	}
@@ -780,7 +1064,7 @@ struct cfb_ctx {
 	Slot slots[kSlots];
 	Counters* d_ctr = nullptr; bool count = false;
 	uint64_t launches = 0;
-	int search_blocks = 0, resolve_blocks = 0, group = 8;
+	int search_blocks = 0, resolve_blocks = 0, group = 1; bool resolve_t = true;
 	cfb_dbatch resident; bool resident_used = false;
 };
 
@@ -846,10 +1130,12 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 	}
 	CKC(cudaMalloc((void**)&c->d_ctr, sizeof(Counters))); CKC(cudaMemset(c->d_ctr, 0, sizeof(Counters)));
 	int occ = 0;
-	{ const char* g = getenv("CFB_GROUP"); if(g) { const int v = atoi(g); if(v == 1 || v == 2 || v == 4 || v == 8) c->group = v; } }
+	{ const char* g = getenv("CFB_GROUP"); if(g) { const int v = atoi(g); if(v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->group = v; } }
 	CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel(c->group, false), kSearchThreads, 0));
 	c->search_blocks = ix->sm_count * std::max(occ, 1);
-	CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
+	{ const char* g = getenv("CFB_RESOLVE_COOP"); if(g && g[0] == '1') c->resolve_t = false; }
+	if(c->resolve_t) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_t<false>, kSearchThreads, 0));
+	else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
 	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
 	const char* cnt = getenv("CFB_COUNT");
 	c->count = cnt && cnt[0] == '1';
@@ -920,10 +1206,14 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 		sa.pk = s.pk.p; sa.nm = s.nm.p; sa.W = W;
 		{ PackArgs pa; pa.b = s.bv; pa.pk = s.pk.p; pa.nm = s.nm.p; pa.W = W;
 		  k_pack<<<(unsigned)((ntasks * W + 127) / 128), 128, 0, s.st>>>(pa); c->launches++; }
-		sa.task_ctr = (unsigned int*)(s.scal.p + 0); sa.ntasks = (uint32_t)ntasks; sa.overflow = (unsigned int*)(s.scal.p + 2); sa.ctr = ctr;
-		const uint64_t per_block = kSearchThreads / c->group;
+		sa.task_ctr = (unsigned int*)(s.scal.p + 0); sa.task_ctr64 = s.scal.p + 0; sa.ntasks = (uint32_t)ntasks; sa.overflow = (unsigned int*)(s.scal.p + 2); sa.ctr = ctr;
+		const uint64_t per_block = kSearchThreads / (c->group == 16 ? 1 : c->group);
 		const uint64_t groups = (uint64_t)c->search_blocks * per_block;
 		uint64_t chunk = ntasks / (groups * 8); sa.chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(chunk, 1), 16);
+		if(c->group == 1) {   // pooled hand-out: one atomic per warp refill of >= 32 tasks
+			const uint64_t warps = (uint64_t)c->search_blocks * (kSearchThreads / 32);
+			sa.chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ntasks / (warps * 4), 32), 256);
+		}
 		const int blocks = (int)std::min<uint64_t>((uint64_t)c->search_blocks, (ntasks + per_block - 1) / per_block);
 		search_kernel(c->group, c->count)<<<blocks, kSearchThreads, 0, s.st>>>(sa);
 		c->launches++;
@@ -937,8 +1227,9 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	k_rows<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
 	if(time_it) CK(cudaEventRecord(s.ev[2], s.st));
 	ResolveArgs ra; ra.v = c->view; ra.rows = s.rows.p; ra.ids = s.ids.p; ra.total = (const uint64_t*)(s.scal.p + 3); ra.rows_cap = s.rows_cap;
-	ra.task_ctr = s.scal.p + 1; ra.chunk = 4; ra.ctr = ctr;
-	if(c->count) k_resolve<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra);
+	ra.task_ctr = s.scal.p + 1; ra.chunk = c->resolve_t ? 128 : 4; ra.ctr = ctr;
+	if(c->resolve_t) { if(c->count) k_resolve_t<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve_t<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
+	else { if(c->count) k_resolve<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
 	c->launches++;
 	if(time_it) CK(cudaEventRecord(s.ev[3], s.st));
 	k_score<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
