@@ -216,10 +216,11 @@ def main():
     base, d = get_index(a.genera, a.species, a.genome_len, 12345, local)
     codes = make_reads(a.genera, a.species, a.genome_len, 12345, a.reads, a.rdlen, 1000 + rank, local)
     n = a.reads
-    bases = codes.reshape(-1)
-    lens = np.full(n, a.rdlen, dtype=np.uint32)
-    offs = np.arange(n, dtype=np.uint64) * np.uint64(a.rdlen)
-    flags = ((codes == 4).sum(axis=1) <= int(0.15 * a.rdlen)).astype(np.uint8)
+    # host buffers of the e2e arm live in pinned memory (cfb_host_alloc), as a real caller's parse buffers would
+    bases = capi.pinned_array((n * a.rdlen,), np.uint8); bases[:] = codes.reshape(-1)
+    lens = capi.pinned_array((n,), np.uint32); lens[:] = a.rdlen
+    offs = capi.pinned_array((n,), np.uint64); offs[:] = np.arange(n, dtype=np.uint64) * np.uint64(a.rdlen)
+    flags = capi.pinned_array((n,), np.uint8); flags[:] = ((codes == 4).sum(axis=1) <= int(0.15 * a.rdlen)).astype(np.uint8)
     batch = capi.make_batch(bases, offs, lens, None, None, flags)
 
     t0 = time.time()

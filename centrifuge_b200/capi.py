@@ -118,6 +118,18 @@ def make_batch(bases, off1, len1, off2=None, len2=None, flags=None):
     return b
 
 
+def pinned_array(shape, dtype):
+    """numpy array backed by cfb_host_alloc (pinned) memory: H2D copies are DMA'd straight from it."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    ptr = lib().cfb_host_alloc(C.c_size_t(max(n, 1)))
+    if not ptr:
+        raise CfbError("cfb_host_alloc failed")
+    buf = (C.c_char * max(n, 1)).from_address(ptr)
+    a = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    return a
+
+
 def _result(res):
     n = int(res.n_units)
     nrec = int(res.n_recs)

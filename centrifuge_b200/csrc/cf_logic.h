@@ -46,6 +46,7 @@ struct IndexView {
 	const uint8_t*  seq_excluded;   // per-sequence flag (per ctx; may be null)
 	const uint64_t* host_taxids;    // sorted expanded host set (per ctx)
 	const uint64_t* blocks;         // device-only re-blocked FM index: 64-byte blocks of 128 rows (cfb200.cu)
+	const uint64_t* rankv;          // device-only per-base rank sectors: 32 bytes per (192 rows, base)
 	uint64_t len, zoff, zside, fchr[4], last_boundary, num_sides, num_blocks;
 	uint32_t zoffc, n_boundaries, n_seqs, n_host;
 	int32_t  off_rate, ftab_chars, bshift;

@@ -426,6 +426,63 @@ __global__ void k_build_blocks(const uint64_t* sides, uint64_t num_sides, uint64
 	for(uint32_t k = 0; k < 4; k++) o[4 + k] = sentinel ? 0ull : sd[part * 4 + k];
 }
 
+// ---------------------------------------------------------------------------------------
+// Per-base rank sectors (the search kernel's view of the index).  For every 192 rows (half a side)
+// and every base c one 32-byte sector:  u64 occ_c before the block | 192 indicator bits BWT[row]==c.
+// LF(row, c) = fchr[c] + occ + popcount(bits below row) touches exactly one 32-byte DRAM sector;
+// the four sectors of a block share one 128-byte line.  The '$' row's bit is cleared in A's vector,
+// so neither the rank nor the mapLF1 test needs a '$' special case.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t even_bits(uint64_t x) {    // gather bits 0,2,4,.. into the low 32 bits
+	x &= 0x5555555555555555ull;
+	x = (x | (x >> 1)) & 0x3333333333333333ull;
+	x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0full;
+	x = (x | (x >> 4)) & 0x00ff00ff00ff00ffull;
+	x = (x | (x >> 8)) & 0x0000ffff0000ffffull;
+	x = (x | (x >> 16)) & 0x00000000ffffffffull;
+	return x;
+}
+__global__ void k_build_rankv(const uint64_t* sides, uint64_t num_sides, uint64_t zside, uint32_t zoffc, uint64_t* rankv) {
+	const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(b > num_sides * 2) return;
+	const bool sentinel = b == num_sides * 2;                 // totals, for an exclusive bound == len+1 on a side boundary
+	const uint64_t s = sentinel ? num_sides - 1 : b >> 1; const uint32_t half = sentinel ? 2u : (uint32_t)(b & 1);
+	const uint64_t* sd = sides + s * 16;
+	uint64_t occ[4] = {sd[12], sd[13], sd[14], sd[15]};
+	for(uint32_t k = 0; k < half * 6; k++) {
+		const uint64_t w = sd[k];
+		const uint64_t lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;
+		const uint32_t c1 = __popcll(lo & ~hi), c2 = __popcll(hi & ~lo), c3 = __popcll(hi & lo);
+		occ[1] += c1; occ[2] += c2; occ[3] += c3; occ[0] += 32 - c1 - c2 - c3;
+	}
+	if(s == zside && zoffc < half * 192) occ[0] -= 1;
+	for(int c = 0; c < 4; c++) {
+		uint64_t bits[3] = {0, 0, 0};
+		if(!sentinel) {
+			for(int k = 0; k < 6; k++) {
+				const uint64_t m = even_bits(match2(sd[half * 6 + k], c));       // 32 indicator bits
+				bits[k >> 1] |= m << (32 * (k & 1));
+			}
+			if(c == 0 && s == zside && zoffc >= half * 192 && zoffc < half * 192 + 192) { const uint32_t z = zoffc - half * 192; bits[z >> 6] &= ~(1ull << (z & 63)); }
+		}
+		uint64_t* o = rankv + (b * 4 + c) * 4;
+		o[0] = occ[c]; o[1] = bits[0]; o[2] = bits[1]; o[3] = bits[2];
+	}
+}
+// rows below `off` (0..191) whose indicator bit is set
+__device__ __forceinline__ uint32_t rankv_count(uint64_t b0, uint64_t b1, uint64_t b2, uint32_t off) {
+	const uint32_t k = off >> 6, part = off & 63;
+	const uint64_t bk = k == 0 ? b0 : (k == 1 ? b1 : b2);
+	uint32_t r = (uint32_t)__popcll(bk & ((1ull << part) - 1ull));
+	if(k > 0) r += (uint32_t)__popcll(b0);
+	if(k > 1) r += (uint32_t)__popcll(b1);
+	return r;
+}
+__device__ __forceinline__ void row_block192(uint64_t row, uint64_t& blk, uint32_t& off) {
+	blk = __umul64hi(row >> 6, 0xAAAAAAAAAAAAAAABull) >> 1;     // (row / 64) / 3
+	off = (uint32_t)(row - blk * 192);
+}
+
 struct Blk { uint64_t m[4]; uint32_t pc[4]; };    // match masks of base c and their popcounts
 
 __device__ __forceinline__ void blk_prep(Blk& q, const ulonglong2& a, const ulonglong2& b, uint64_t rep) {
@@ -454,8 +511,7 @@ template <bool COUNT, int MB>
 __global__ void __launch_bounds__(kSearchThreads, MB) k_search_t(const SearchArgs a) {
 	SearchCtx<COUNT, 1> cx(a);
 	cx.pooled = true;
-	const uint64_t* blocks = a.v.blocks;
-	const uint64_t zblk = a.v.zoff >> 7; const uint32_t zoffb = (uint32_t)(a.v.zoff & 127);
+	const uint64_t* rankv = a.v.rankv;
 	Walk2 w; memset(&w, 0, sizeof w); w.mode = M_NEED;
 	WarpPool pool; pool.base = pool.end = 0;
 	bool more = true;      // warp-uniform: the global task counter is not exhausted yet
@@ -476,7 +532,7 @@ __global__ void __launch_bounds__(kSearchThreads, MB) k_search_t(const SearchArg
 		}
 		if(!__any_sync(0xffffffffu, w.mode != M_DONE)) break;
 		int c = 4;
-		uint64_t e0 = 0, e1 = 0, occT = 0, occB = 0;
+		uint64_t e0 = 0, e1 = 0;
 		ulonglong2 t0, t1, b0, b1;
 		t0 = t1 = b0 = b1 = make_ulonglong2(0, 0);
 		const bool lf = w.mode == M_LF;
@@ -491,16 +547,13 @@ __global__ void __launch_bounds__(kSearchThreads, MB) k_search_t(const SearchArg
 			c = ((nw >> sh) & 1u) ? 4 : (int)((rw >> (2 * sh)) & 3);
 			if(c <= 3) {
 				range = (w.bot - w.top) != 1;
-				bT = w.top >> 7; oT = (uint32_t)(w.top & 127);
-				bB = w.bot >> 7; oB = (uint32_t)(w.bot & 127);
-				same = !range || bB == bT;
-				const uint64_t* pt = blocks + bT * 8;
-				occT = __ldg(pt + c);
-				t0 = __ldg(reinterpret_cast<const ulonglong2*>(pt + 4)); t1 = __ldg(reinterpret_cast<const ulonglong2*>(pt + 6));
-				if(!same) {
-					const uint64_t* pb = blocks + bB * 8;
-					occB = __ldg(pb + c);
-					b0 = __ldg(reinterpret_cast<const ulonglong2*>(pb + 4)); b1 = __ldg(reinterpret_cast<const ulonglong2*>(pb + 6));
+				row_block192(w.top, bT, oT);
+				const ulonglong2* pt = reinterpret_cast<const ulonglong2*>(rankv + (bT * 4 + c) * 4);
+				t0 = __ldg(pt); t1 = __ldg(pt + 1);                         // {occ, bits0} {bits1, bits2}
+				if(range) {
+					row_block192(w.bot, bB, oB);
+					same = bB == bT;
+					if(!same) { const ulonglong2* pb = reinterpret_cast<const ulonglong2*>(rankv + (bB * 4 + c) * 4); b0 = __ldg(pb); b1 = __ldg(pb + 1); }
 				}
 			}
 		}
@@ -519,22 +572,14 @@ __global__ void __launch_bounds__(kSearchThreads, MB) k_search_t(const SearchArg
 			bool fail = c > 3;
 			uint64_t t = 0, b = 0;
 			if(!fail) {
-				const uint64_t rep = (uint64_t)c * 0x5555555555555555ull;
-				Blk qT, qB;
-				blk_prep(qT, t0, t1, rep);
-				if(same) { qB = qT; occB = occT; } else blk_prep(qB, b0, b1, rep);
-				uint64_t rT = blk_rank(qT, oT), rB = blk_rank(qB, oB);
-				if(c == 0) {
-					if(bT == zblk && zoffb < oT) rT--;
-					if(bB == zblk && zoffb < oB) rB--;
-				}
-				t = a.v.fchr[c] + occT + rT;
-				b = range ? a.v.fchr[c] + occB + rB : t + 1;
-				if(!range) {                              // mapLF1 bt2_idx.h:2910-2933: BWT[top] must be c
-					const uint32_t k = oT >> 5;
-					const uint64_t wk = k == 0 ? t0.x : (k == 1 ? t0.y : (k == 2 ? t1.x : t1.y));
-					const int rowc = (int)((wk >> (2 * (oT & 31))) & 3);
-					if(rowc != c || w.top == a.v.zoff) fail = true;
+				if(same) { b0 = t0; b1 = t1; }
+				t = a.v.fchr[c] + t0.x + rankv_count(t0.y, t1.x, t1.y, oT);
+				if(range) b = a.v.fchr[c] + b0.x + rankv_count(b0.y, b1.x, b1.y, oB);
+				else {                                    // mapLF1 bt2_idx.h:2910-2933: BWT[top] must be c ('$' has no bit)
+					const uint32_t k = oT >> 6;
+					const uint64_t bk = k == 0 ? t0.y : (k == 1 ? t1.x : t1.y);
+					if(!((bk >> (oT & 63)) & 1ull)) fail = true;
+					b = t + 1;
 				}
 				if(b <= t) fail = true;
 				if(COUNT) {   // counters keep the reference's side geometry (384 rows per 128-byte side)
@@ -992,6 +1037,14 @@ extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out)
 			CK(cudaDeviceSynchronize());
 			v.blocks = blk; v.num_blocks = nb;
 		}
+		{   // per-base rank sectors for the search kernel
+			uint64_t* rv = nullptr; const uint64_t nb = h.num_sides * 2;
+			CK(cudaMalloc((void**)&rv, (nb + 1) * 128));
+			ix->dptrs.push_back(rv); ix->device_bytes += (nb + 1) * 128;
+			k_build_rankv<<<(unsigned)((nb + 1 + 255) / 256), 256>>>(v.sides, h.num_sides, v.zside, v.zoffc, rv);
+			CK(cudaDeviceSynchronize());
+			v.rankv = rv;
+		}
 		// host copies of the big arrays are no longer needed once uploaded
 		std::vector<uint8_t>().swap(ix->h.sides);
 	}
@@ -1158,15 +1211,27 @@ static int stage_batch(cfb_ctx* c, Slot& s, const cfb_batch* b) {
 		maxlen = std::max(maxlen, b->len[m][i]);
 	}
 	if(maxlen > 60000) return fail(CFB_EINVAL, "read longer than 60000 bases");
-	CK(s.h_bases.ensure(b->n_bases)); CK(s.h_off.ensure(n * nm)); CK(s.h_len.ensure(n * nm)); CK(s.h_flags.ensure(n));
 	CK(s.d_bases.ensure(b->n_bases + 16)); CK(s.d_off.ensure(n * nm)); CK(s.d_len.ensure(n * nm)); CK(s.d_flags.ensure(n));
-	memcpy(s.h_bases.p, b->bases, b->n_bases);
-	for(int m = 0; m < nm; m++) { memcpy(s.h_off.p + m * n, b->off[m], n * 8); memcpy(s.h_len.p + m * n, b->len[m], n * 4); }
-	if(b->flags) memcpy(s.h_flags.p, b->flags, n); else memset(s.h_flags.p, 3, n);
-	CK(cudaMemcpyAsync(s.d_bases.p, s.h_bases.p, b->n_bases, cudaMemcpyHostToDevice, s.st));
-	CK(cudaMemcpyAsync(s.d_off.p, s.h_off.p, n * nm * 8, cudaMemcpyHostToDevice, s.st));
-	CK(cudaMemcpyAsync(s.d_len.p, s.h_len.p, n * nm * 4, cudaMemcpyHostToDevice, s.st));
-	CK(cudaMemcpyAsync(s.d_flags.p, s.h_flags.p, n, cudaMemcpyHostToDevice, s.st));
+	// Caller arrays that already live in pinned memory (cfb_host_alloc) are DMA'd from where they are and
+	// must stay untouched until cfb_classify_wait; pageable arrays are staged through pinned buffers first.
+	auto pinned = [](const void* p) -> bool {
+		cudaPointerAttributes at;
+		if(cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+		return at.type == cudaMemoryTypeHost;
+	};
+	const uint8_t* src_bases = b->bases;
+	if(!pinned(b->bases)) { CK(s.h_bases.ensure(b->n_bases)); memcpy(s.h_bases.p, b->bases, b->n_bases); src_bases = s.h_bases.p; }
+	CK(cudaMemcpyAsync(s.d_bases.p, src_bases, b->n_bases, cudaMemcpyHostToDevice, s.st));
+	CK(s.h_off.ensure(n * nm)); CK(s.h_len.ensure(n * nm)); CK(s.h_flags.ensure(n));
+	for(int m = 0; m < nm; m++) {
+		const uint64_t* so = b->off[m]; const uint32_t* sl = b->len[m];
+		if(!pinned(so)) { memcpy(s.h_off.p + m * n, so, n * 8); so = s.h_off.p + m * n; }
+		if(!pinned(sl)) { memcpy(s.h_len.p + m * n, sl, n * 4); sl = s.h_len.p + m * n; }
+		CK(cudaMemcpyAsync(s.d_off.p + m * n, so, n * 8, cudaMemcpyHostToDevice, s.st));
+		CK(cudaMemcpyAsync(s.d_len.p + m * n, sl, n * 4, cudaMemcpyHostToDevice, s.st));
+	}
+	if(b->flags && pinned(b->flags)) CK(cudaMemcpyAsync(s.d_flags.p, b->flags, n, cudaMemcpyHostToDevice, s.st));
+	else { if(b->flags) memcpy(s.h_flags.p, b->flags, n); else memset(s.h_flags.p, 3, n); CK(cudaMemcpyAsync(s.d_flags.p, s.h_flags.p, n, cudaMemcpyHostToDevice, s.st)); }
 	s.bv.bases = s.d_bases.p; s.bv.flags = s.d_flags.p; s.bv.n_units = (uint32_t)n; s.bv.n_mates = nm;
 	for(int m = 0; m < 2; m++) { s.bv.off[m] = m < nm ? s.d_off.p + m * n : nullptr; s.bv.len[m] = m < nm ? s.d_len.p + m * n : nullptr; }
 	s.n_units = n; s.n_bases = b->n_bases; s.maxlen = maxlen;

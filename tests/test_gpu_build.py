@@ -106,3 +106,28 @@ def test_builder_many_sequences_wide_sample(tmp_path):
     ref_build(d + "/g.fa", d + "/conv.tsv", d + "/nodes.dmp", d + "/names.dmp", d + "/ref")
     m.build_index(m.build_opts(d + "/mine", fasta=[d + "/g.fa"], conversion_table=d + "/conv.tsv", taxonomy_tree=d + "/nodes.dmp", name_table=d + "/names.dmp"))
     assert_same_index(d + "/ref", d + "/mine")
+
+
+def test_bench_data_path_matches_reference_end_to_end(tmp_path):
+    """The exact pipeline bench.py times -- index from cfb_build_index (synthetic mode), reads from
+    cfb_synth_reads, classification through the drop-in CLI -- equals the unmodified reference binary
+    run on the same index files and reads, byte for byte (TSV and report)."""
+    import sys
+    sys.path.insert(0, util.ROOT)
+    import bench
+    m = capi()
+    d = str(tmp_path)
+    g, s, L = 12, 5, 400000
+    tax = m.write_synth_taxonomy(d, g, s, L)
+    o = m.build_opts(d + "/idx", synth=(g, s, L, 4242, 0.03), conversion_table=tax[0], taxonomy_tree=tax[1], name_table=tax[2])
+    m.build_index(o)
+    codes = m.synth_reads(o, 30000, 100, 17)
+    fq = d + "/r.fq"
+    bench.write_fastq(fq, codes)
+    exe = os.path.join(util.ROOT, "centrifuge_b200", "centrifuge-class")
+    a = util.run_cli(util.REF_CLASS, ["-q", "-x", d + "/idx", "-U", fq], d + "/a.tsv", d + "/a.rep")
+    b = util.run_cli(exe, ["-q", "-x", d + "/idx", "-U", fq, "--batch-units", "7000"], d + "/b.tsv", d + "/b.rep")
+    assert a[0] == b[0]
+    assert a[1] == b[1]
+    rows = a[0].decode().strip().split("\n")[1:]
+    assert sum(1 for r in rows if "unclassified" not in r) > 25000      # the synthetic reads do classify
