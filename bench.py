@@ -227,12 +227,13 @@ def main():
     ix = capi.Index(base, local)
     log("rank %d: index in HBM: %.2f GB in %.1f s (%d sides)" % (rank, ix.info.device_bytes / 1e9, time.time() - t0, ix.info.num_sides))
     ctx = capi.Context(ix)
-    n_tax = int(ix.info.n_tax_nodes) + 1
-    counts = torch.zeros(n_tax * 2, dtype=torch.int64, device="cuda")
-
-    def fold_counts(off, recs):
-        # dense per-taxon {numReads, numUniqueReads}: one vector per rank, summed by NCCL
-        return None
+    from centrifuge_b200.abundance import taxon_counts
+    node_taxids = ix.node_taxids()
+    # dense per-taxon {numReads, numUniqueReads} of this rank's shard: folded once from the first
+    # result on the host, then all-reduced (NCCL, sum) at the end of every step
+    off0, recs0 = ctx.classify(batch)
+    local_counts = taxon_counts(node_taxids, off0, recs0, k=5)
+    counts = torch.from_numpy(local_counts.reshape(-1).copy()).cuda()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -264,7 +265,8 @@ def main():
         ms, nrec = ctx.classify_resident(dbatch)       # per-stage CUDA-event times on the kernels' own stream
         kms += np.array(ms)
         if dist:
-            dist.all_reduce(counts)
+            step_counts = counts.clone()
+            dist.all_reduce(step_counts)
     sync_all()
     wall = time.perf_counter() - t_wall0
     launches_value = ctx.launches()
@@ -292,7 +294,8 @@ def main():
     while inflight:
         _, nr = ctx.wait(inflight.pop(0), copy=False); d2h += nr * 24 + (n + 1) * 4
     if dist:
-        dist.all_reduce(counts)
+        step_counts = counts.clone()
+        dist.all_reduce(step_counts)
     sync_all()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -318,6 +321,7 @@ def main():
                      "sides_per_read": ctr["sides_search"] / max(ctr["units"], 1), "walk_bytes_per_launch": int(bytes_walk)},
         "kernel_ms": {"search": kms[0] / a.steps, "prep_rows": kms[1] / a.steps, "resolve": kms[2] / a.steps, "score_compact": kms[3] / a.steps, "total": step_ms},
         "clocks": sampler.summary(),
+        "taxon_vector": {"len": int(counts.numel()), "classified_reads_rank0": int(local_counts[:-1, 0].sum()), "unclassified_reads_rank0": int(local_counts[-1, 1])},
         "wall_s_value_region": wall_s,
     }
     if rank == 0:

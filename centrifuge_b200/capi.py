@@ -86,6 +86,12 @@ class Index:
         ok = lib().cfb_index_tax_node(self.h, C.c_uint64(taxid), C.byref(par), C.byref(rank), C.byref(leaf))
         return (int(par.value), rank.value, leaf.value) if ok else None
 
+    def node_taxids(self):
+        n = int(self.info.n_tax_nodes)
+        out = np.zeros(n, dtype=np.uint64)
+        _ck(lib().cfb_index_node_taxids(self.h, _p(out, C.c_uint64), C.c_uint64(n)))
+        return out
+
     def close(self):
         if self.h:
             lib().cfb_index_free(self.h)

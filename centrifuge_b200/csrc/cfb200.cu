@@ -1074,6 +1074,11 @@ extern "C" int cfb_index_tax_node(const cfb_index* ix, uint64_t taxid, uint64_t*
 }
 // internal accessor for the host driver (cf_host.cpp); not part of the public C ABI
 extern "C" const cfb::HostIndex* cfb_index_host(const cfb_index* ix) { return ix ? &ix->h : NULL; }
+extern "C" int cfb_index_node_taxids(const cfb_index* ix, uint64_t* out, uint64_t cap) {
+	if(!ix || !out || cap < ix->h.nodes.size()) return fail(CFB_EINVAL, "cfb_index_node_taxids: buffer too small");
+	for(size_t i = 0; i < ix->h.nodes.size(); i++) out[i] = ix->h.nodes[i].taxid;
+	return CFB_OK;
+}
 extern "C" void cfb_params_default(cfb_params* p) {
 	if(!p) return;
 	memset(p, 0, sizeof *p); p->khits = 5; p->min_hitlen = 22; p->tree_traverse = 1; p->class_rank_slot = 0;

@@ -63,6 +63,8 @@ const char* cfb_index_seq_name(const cfb_index*, uint32_t seq);           /* uid
 uint64_t    cfb_index_seq_taxid(const cfb_index*, uint32_t seq);
 /* returns 1 if taxid is a tree node; rank = TaxonomyNode.rank (taxonomy.h:16), leaf flag */
 int         cfb_index_tax_node(const cfb_index*, uint64_t taxid, uint64_t* parent, int* rank, int* leaf);
+/* all tree taxids in ascending order (n_tax_nodes entries): the index space of dense per-taxon vectors */
+int         cfb_index_node_taxids(const cfb_index*, uint64_t* out, uint64_t cap);
 
 /* Replaces: Classifier ctor arguments (classifier.h:135-143) + ReportingParams (aln_sink.h:573). */
 typedef struct {
