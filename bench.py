@@ -83,30 +83,38 @@ def write_fastq(path, codes, prefix="r"):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed regions, via NVML in-process (no nvidia-smi forks, which
+    contend for the driver lock with the CUDA calls being timed)."""
+
     def __init__(self, dev):
         super().__init__(daemon=True)
         self.dev, self.samples, self.reasons, self.stop_flag, self.maxmhz = dev, [], set(), False, None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0])); self.maxmhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.dev)
+            self.maxmhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                    "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for nm, b in bits.items():
+                    if b and (r & b):
                         self.reasons.add(nm)
-            except Exception:
-                pass
-            time.sleep(0.2)
+                time.sleep(0.05)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add("nvml_unavailable: %s" % e)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons)}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 def ref_reads_per_s(base, fq, threads):

@@ -47,9 +47,12 @@ struct IndexView {
 	const uint64_t* host_taxids;    // sorted expanded host set (per ctx)
 	const uint64_t* blocks;         // device-only re-blocked FM index: 64-byte blocks of 128 rows (cfb200.cu)
 	const uint64_t* rankv;          // device-only per-base rank sectors: 32 bytes per (192 rows, base)
+	const uint64_t* rank16;         // device-only rank entries: 16 bytes (occ_c, 64 indicator bits) per (64 rows, base)
+	const uint64_t* ftab2;          // device-only fused ftab: (top, bot) per 10-mer, eftab already resolved
+	const uint64_t* ftabk;          // device-only extended jump table: (top, bot) per K-mer, K = ftabk_chars (0 = absent)
 	uint64_t len, zoff, zside, fchr[4], last_boundary, num_sides, num_blocks;
 	uint32_t zoffc, n_boundaries, n_seqs, n_host;
-	int32_t  off_rate, ftab_chars, bshift;
+	int32_t  off_rate, ftab_chars, bshift, ftabk_chars;
 };
 
 struct Params {

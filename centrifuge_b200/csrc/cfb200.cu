@@ -17,7 +17,7 @@ using namespace cfb;
 // =======================================================================================
 // k_search
 // =======================================================================================
-enum { M_DONE = 0, M_FTAB = 1, M_LF = 2, M_NEED = 3 };
+enum { M_DONE = 0, M_FTAB = 1, M_LF = 2, M_NEED = 3, M_FTABK = 4 };
 
 struct Walk {            // group-uniform state of one greedy strand walk
 	const uint8_t* fw; uint32_t rlen; int strand; uint32_t tid;
@@ -483,6 +483,72 @@ __device__ __forceinline__ void row_block192(uint64_t row, uint64_t& blk, uint32
 	off = (uint32_t)(row - blk * 192);
 }
 
+// ---------------------------------------------------------------------------------------
+// rank16: the layout both walk kernels use.  For every 64 rows and every base c one 16-byte entry
+//   u64 occ_c (count of c before the block, '$' excluded; bit 63 of A's entry = "block holds a genome-
+//   boundary row")  |  u64 indicator bits (BWT[row] == c; the '$' row has no bit)
+// so LF(row, c) = fchr[c] + occ + popc(bits & lowmask(row & 63)) costs ONE 16-byte load request.
+// Measured on this part (tools/gather_bench.cu): fully divergent gathers are capped at ~70 G 16-byte
+// lane requests/s independent of size (32 B: 34 G/s, 64 B: 17.6 G/s, 128 B: 8.9 G/s), so requests per
+// LF step -- not bytes -- is what bounds the walk.  The four bases of a block share one 64-byte chunk.
+// ---------------------------------------------------------------------------------------
+__global__ void k_build_rank16(const uint64_t* sides, uint64_t num_sides, uint64_t zside, uint32_t zoffc, uint64_t* r16) {
+	const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(b > num_sides * 6) return;
+	const bool sentinel = b == num_sides * 6;                 // totals, for an exclusive bound == len+1 on a side boundary
+	const uint64_t s = sentinel ? num_sides - 1 : b / 6; const uint32_t sub = sentinel ? 6u : (uint32_t)(b - s * 6);
+	const uint64_t* sd = sides + s * 16;
+	uint64_t occ[4] = {sd[12], sd[13], sd[14], sd[15]};
+	for(uint32_t k = 0; k < sub * 2; k++) {
+		const uint64_t w = sd[k];
+		const uint64_t lo = w & 0x5555555555555555ull, hi = (w >> 1) & 0x5555555555555555ull;
+		const uint32_t c1 = __popcll(lo & ~hi), c2 = __popcll(hi & ~lo), c3 = __popcll(hi & lo);
+		occ[1] += c1; occ[2] += c2; occ[3] += c3; occ[0] += 32 - c1 - c2 - c3;
+	}
+	if(s == zside && zoffc < sub * 64) occ[0] -= 1;
+	for(int c = 0; c < 4; c++) {
+		uint64_t bits = 0;
+		if(!sentinel) {
+			bits = even_bits(match2(sd[sub * 2], c)) | (even_bits(match2(sd[sub * 2 + 1], c)) << 32);
+			if(c == 0 && s == zside && zoffc >= sub * 64 && zoffc < sub * 64 + 64) bits &= ~(1ull << (zoffc - sub * 64));
+		}
+		r16[(b * 4 + c) * 2] = occ[c]; r16[(b * 4 + c) * 2 + 1] = bits;
+	}
+}
+__global__ void k_mark_boundaries(const uint64_t* brow, uint32_t n, uint64_t* r16) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n) atomicOr((unsigned long long*)&r16[(brow[i] >> 6) * 8], 1ull << 63);
+}
+__global__ void k_build_ftab2(IndexView v, uint64_t n, uint64_t* ftab2) {
+	const uint64_t fi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(fi >= n) return;
+	ftab2[fi * 2] = ftab_hi(v, v.ftab[fi]); ftab2[fi * 2 + 1] = ftab_lo(v, v.ftab[fi + 1]);
+}
+static const uint64_t kOccMask = 0x7fffffffffffffffull;
+
+// Extended jump table: the SA range of every K-mer (K > ftabChars), obtained by K - ftabChars LF steps from the
+// 10-mer range -- exactly what partialSearch would compute base by base (hi_aligner.h:985-1008).  It trades
+// HBM capacity (16 B x 4^K; 17 GB at K = 15) for random accesses: one gather replaces K - 10 walk steps whose
+// top and bot rows are far apart (two DRAM sectors each).  An empty entry (bot <= top) only says the range
+// died somewhere in between; the kernel then redoes that search from the 10-mer table to find where.
+__global__ void k_build_ftabk(IndexView v, int K, uint64_t n, uint64_t* out) {
+	const uint64_t fk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(fk >= n) return;
+	const ulonglong2* r16 = reinterpret_cast<const ulonglong2*>(v.rank16);
+	const int fc = v.ftab_chars;
+	const uint64_t f10 = fk & ((1ull << (2 * fc)) - 1ull);
+	uint64_t top = v.ftab2[f10 * 2], bot = v.ftab2[f10 * 2 + 1];
+	for(int j = fc; j < K && bot > top; j++) {
+		const int c = (int)((fk >> (2 * j)) & 3);
+		const ulonglong2 tq = __ldg(r16 + (top >> 6) * 4 + c), bq = __ldg(r16 + (bot >> 6) * 4 + c);
+		top = v.fchr[c] + (tq.x & kOccMask) + (uint64_t)__popcll(tq.y & ((1ull << (top & 63)) - 1ull));
+		bot = v.fchr[c] + (bq.x & kOccMask) + (uint64_t)__popcll(bq.y & ((1ull << (bot & 63)) - 1ull));
+	}
+	if(bot <= top) { top = 0; bot = 0; }
+	out[fk * 2] = top; out[fk * 2 + 1] = bot;
+}
+
+
 struct Blk { uint64_t m[4]; uint32_t pc[4]; };    // match masks of base c and their popcounts
 
 __device__ __forceinline__ void blk_prep(Blk& q, const ulonglong2& a, const ulonglong2& b, uint64_t rep) {
@@ -503,113 +569,189 @@ __device__ __forceinline__ uint32_t blk_rank(const Blk& q, uint32_t off) {
 }
 
 // ---------------------------------------------------------------------------------------
-// k_search_t: one thread per walk.  No cross-lane traffic: each lane reads the 64-byte blocks of its
-// own top and bot rows.  Range and single-row steps share one code path, so the 32 independent walks
-// of a warp diverge only on the restart / ftab paths.
+// k_search_t: one thread per walk.  No cross-lane traffic: each lane reads the 32-byte rank sectors of
+// its own top and bot rows.  Range and single-row steps share one code path, so the 32 independent
+// walks of a warp diverge only on the restart / ftab paths, and those paths contain no blocking loads:
+// the packed strand of the current task lives in registers (RW words, reads up to 32*RW bases), so the
+// per-step base, the N test and the 10-mer ftab index are register extracts.  One loop iteration =
+// one DRAM round trip for every walk of the warp.
 // ---------------------------------------------------------------------------------------
-template <bool COUNT, int MB>
-__global__ void __launch_bounds__(kSearchThreads, MB) k_search_t(const SearchArgs a) {
-	SearchCtx<COUNT, 1> cx(a);
-	cx.pooled = true;
-	const uint64_t* rankv = a.v.rankv;
-	Walk2 w; memset(&w, 0, sizeof w); w.mode = M_NEED;
+template <int RW> struct ReadRegs {
+	uint64_t rw[RW]; uint32_t nw[RW];
+	__device__ __forceinline__ void load(const uint64_t* pk, const uint32_t* nm, uint32_t W) {
+		#pragma unroll
+		for(int k = 0; k < RW; k++) { rw[k] = (uint32_t)k < W ? __ldg(pk + k) : 0ull; nw[k] = (uint32_t)k < W ? __ldg(nm + k) : 0u; }
+	}
+	__device__ __forceinline__ uint64_t word(uint32_t k) const {
+		uint64_t v = 0;
+		#pragma unroll
+		for(int q = 0; q < RW; q++) if((uint32_t)q == k) v = rw[q];
+		return v;
+	}
+	__device__ __forceinline__ uint32_t nword(uint32_t k) const {
+		uint32_t v = 0;
+		#pragma unroll
+		for(int q = 0; q < RW; q++) if((uint32_t)q == k) v = nw[q];
+		return v;
+	}
+	// base at search depth p (4 = N)
+	__device__ __forceinline__ int base(uint32_t p) const {
+		const uint32_t k = p >> 5, sh = p & 31;
+		return ((nword(k) >> sh) & 1u) ? 4 : (int)((word(k) >> (2 * sh)) & 3);
+	}
+	// bases p .. p+31 (base p in the low bits) and their N bits
+	__device__ __forceinline__ void window(uint32_t p, uint64_t& win, uint32_t& nwin) const {
+		const uint32_t k = p >> 5, sh = p & 31;
+		win = shr64(word(k), 2 * sh) | shl64(word(k + 1), 64 - 2 * sh);
+		nwin = (uint32_t)(((uint64_t)nword(k) | ((uint64_t)nword(k + 1) << 32)) >> sh);
+	}
+};
+
+template <bool COUNT, int RW>
+__global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a) {
+	const ulonglong2* r16 = reinterpret_cast<const ulonglong2*>(a.v.rank16);
+	const ulonglong2* ftab2 = reinterpret_cast<const ulonglong2*>(a.v.ftab2);
+	const ulonglong2* ftabk = reinterpret_cast<const ulonglong2*>(a.v.ftabk);
+	const uint32_t fk = (COUNT || !a.v.ftabk) ? 0u : (uint32_t)a.v.ftabk_chars;   // counters follow the reference's op sequence
+	const uint32_t fc = (uint32_t)a.v.ftab_chars;
+	ReadRegs<RW> rd;
+	uint64_t top = 0, bot = 0, fi = 0;
+	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0;
+	int mode = M_NEED;
+	unsigned long long c_ps = 0, c_ft = 0, c_sides = 0, c_lf = 0;
 	WarpPool pool; pool.base = pool.end = 0;
 	bool more = true;      // warp-uniform: the global task counter is not exhausted yet
+
+	auto emit = [&](uint64_t t, uint64_t b, uint32_t off, uint32_t len) {
+		if(nh < a.cap) { HitRec* h = a.hits + (size_t)tid * a.cap + nh; h->top = t; h->bot = b; h->bwoff = off; h->len = len; }
+		else atomicExch(a.overflow, 1u);
+		nh++;
+	};
+	// searchForwardAndReverse restart policy (classifier.h:686-766): true = another partial search starts at cur
+	auto after_hit = [&](uint32_t hlen) -> bool {
+		bool done = cur >= rlen;
+		if(!done) { if(hlen > a.p.increment) cur += 1; if(cur + a.p.min_hitlen >= rlen) done = true; }
+		if(done) { a.nhits[tid] = nh; mode = M_NEED; return false; }
+		return true;
+	};
+	// partialSearch prologue (hi_aligner.h:939-982) at `cur`: ends in M_FTAB (fi set) or M_NEED
+	auto start_search = [&]() {
+		for(;;) {
+			if(COUNT) c_ps++;
+			offset = cur;
+			if(rlen - cur < fc) { emit(kOff, kOff, offset, rlen - offset); a.nhits[tid] = nh; mode = M_NEED; return; }
+			uint64_t win; uint32_t nwin; rd.window(cur, win, nwin);
+			const uint32_t nbits = nwin & ((1u << fc) - 1u);
+			if(nbits) {
+				const uint32_t hl = (uint32_t)__ffs(nbits);
+				cur += hl;
+				emit(kOff, kOff, offset, hl);
+				if(after_hit(hl)) continue; else return;
+			}
+			if(fk && rlen - cur >= fk && !(nwin & ((1u << fk) - 1u))) { fi = win & ((1ull << (2 * fk)) - 1ull); mode = M_FTABK; return; }
+			fi = win & ((1ull << (2 * fc)) - 1ull);
+			mode = M_FTAB;
+			return;
+		}
+	};
+	auto hit_and_restart = [&]() {
+		const uint32_t hl = dep - offset;
+		emit(top, bot, offset, hl);
+		cur = dep;
+		if(after_hit(hl)) start_search();
+	};
 
 	for(;;) {
 		// ---------------- hand out tasks (convergent point) ----------------
 		{
-			const bool want = w.mode == M_NEED;
+			const bool want = mode == M_NEED;
 			if(more) {
 				unsigned long long t = 0;
 				const bool got = pool_take(pool, want, a.task_ctr64, (unsigned long long)a.ntasks, a.chunk, t);
 				if(want) {
-					if(got) { w.tid = (uint32_t)t; if(cx.bind_task(w)) cx.start_search(w); }   // filtered mate: stays M_NEED
-					else w.mode = M_DONE;
+					if(got) {
+						tid = (uint32_t)t;
+						const uint32_t per = 2u * (uint32_t)a.b.n_mates;
+						const uint32_t unit = tid / per, rem = tid - unit * per;
+						const int mate = (int)(rem >> 1);
+						const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
+						nh = 0; rlen = a.b.len[mate][unit];
+						if(!((fl >> mate) & 1) || rlen == 0) a.nhits[tid] = 0;          // filtered mate: stays M_NEED
+						else { rd.load(a.pk + (size_t)tid * a.W, a.nm + (size_t)tid * a.W, a.W); cur = 0; start_search(); }
+					} else mode = M_DONE;
 				}
 				if(__any_sync(0xffffffffu, want && !got)) more = false;      // global counter ran past the end
-			} else if(want) w.mode = M_DONE;
+			} else if(want) mode = M_DONE;
 		}
-		if(!__any_sync(0xffffffffu, w.mode != M_DONE)) break;
+		if(!__any_sync(0xffffffffu, mode != M_DONE)) break;
+		// ---------------- single fetch point ----------------
 		int c = 4;
-		uint64_t e0 = 0, e1 = 0;
-		ulonglong2 t0, t1, b0, b1;
-		t0 = t1 = b0 = b1 = make_ulonglong2(0, 0);
-		const bool lf = w.mode == M_LF;
-		bool range = false, same = true;
-		uint64_t bT = 0, bB = 0; uint32_t oT = 0, oB = 0;
-		if(w.mode == M_FTAB) { e0 = __ldg(a.v.ftab + w.fi); e1 = __ldg(a.v.ftab + w.fi + 1); }
+		ulonglong2 e = make_ulonglong2(0, 0), tq = e, bq = e;
+		const bool lf = mode == M_LF;
+		bool range = false;
+		if(mode == M_FTAB) e = __ldg(ftab2 + fi);                           // (top, bot) of the 10-mer: one request
+		else if(mode == M_FTABK) e = __ldg(ftabk + fi);                     // (top, bot) of the K-mer
 		else if(lf) {
-			const uint32_t wi = w.dep >> 5;
-			if(wi != w.rwi && wi != w.rwi + 1) cx.load_words(w, wi);
-			const uint32_t sh = w.dep & 31;
-			const uint64_t rw = wi == w.rwi ? w.rw0 : w.rw1; const uint32_t nw = wi == w.rwi ? w.nw0 : w.nw1;
-			c = ((nw >> sh) & 1u) ? 4 : (int)((rw >> (2 * sh)) & 3);
+			c = rd.base(dep);
 			if(c <= 3) {
-				range = (w.bot - w.top) != 1;
-				row_block192(w.top, bT, oT);
-				const ulonglong2* pt = reinterpret_cast<const ulonglong2*>(rankv + (bT * 4 + c) * 4);
-				t0 = __ldg(pt); t1 = __ldg(pt + 1);                         // {occ, bits0} {bits1, bits2}
-				if(range) {
-					row_block192(w.bot, bB, oB);
-					same = bB == bT;
-					if(!same) { const ulonglong2* pb = reinterpret_cast<const ulonglong2*>(rankv + (bB * 4 + c) * 4); b0 = __ldg(pb); b1 = __ldg(pb + 1); }
-				}
+				range = (bot - top) != 1;
+				tq = __ldg(r16 + (top >> 6) * 4 + c);                       // (occ, bits): one request per rank query
+				bq = tq;
+				if(range && (bot >> 6) != (top >> 6)) bq = __ldg(r16 + (bot >> 6) * 4 + c);
 			}
 		}
-		if(w.mode == M_FTAB) {
-			if(COUNT) cx.c_ft++;
-			w.top = ftab_hi(a.v, e0); w.bot = ftab_lo(a.v, e1);
-			w.dep = w.cur + (uint32_t)a.v.ftab_chars;
-			if(w.bot <= w.top) {
-				const uint32_t hl = w.dep - w.offset;
-				cx.emit(w, kOff, kOff, w.offset, hl);
-				w.cur = w.dep;
-				if(cx.after_hit(w, hl)) cx.start_search(w);
-			} else if(w.dep < w.rlen) w.mode = M_LF;
-			else cx.hit_and_restart(w);
+		// ---------------- consume ----------------
+		if(mode == M_FTABK) {
+			if(e.y > e.x) {                               // same state partialSearch reaches after K bases
+				top = e.x; bot = e.y; dep = cur + fk;
+				if(dep < rlen) mode = M_LF; else hit_and_restart();
+			} else { fi &= (1ull << (2 * fc)) - 1ull; mode = M_FTAB; }   // died between base fc and K: replay from the 10-mer
+		} else if(mode == M_FTAB) {
+			if(COUNT) c_ft++;
+			top = e.x; bot = e.y;
+			dep = cur + fc;
+			if(bot <= top) {                              // hi_aligner.h:971-982
+				const uint32_t hl = dep - offset;
+				emit(kOff, kOff, offset, hl);
+				cur = dep;
+				if(after_hit(hl)) start_search();
+			} else if(dep < rlen) mode = M_LF;
+			else hit_and_restart();
 		} else if(lf) {
 			bool fail = c > 3;
 			uint64_t t = 0, b = 0;
 			if(!fail) {
-				if(same) { b0 = t0; b1 = t1; }
-				t = a.v.fchr[c] + t0.x + rankv_count(t0.y, t1.x, t1.y, oT);
-				if(range) b = a.v.fchr[c] + b0.x + rankv_count(b0.y, b1.x, b1.y, oB);
+				const uint32_t oT = (uint32_t)(top & 63), oB = (uint32_t)(bot & 63);
+				t = a.v.fchr[c] + (tq.x & kOccMask) + (uint64_t)__popcll(tq.y & ((1ull << oT) - 1ull));
+				if(range) b = a.v.fchr[c] + (bq.x & kOccMask) + (uint64_t)__popcll(bq.y & ((1ull << oB) - 1ull));
 				else {                                    // mapLF1 bt2_idx.h:2910-2933: BWT[top] must be c ('$' has no bit)
-					const uint32_t k = oT >> 6;
-					const uint64_t bk = k == 0 ? t0.y : (k == 1 ? t1.x : t1.y);
-					if(!((bk >> (oT & 63)) & 1ull)) fail = true;
+					if(!((tq.y >> oT) & 1ull)) fail = true;
 					b = t + 1;
 				}
 				if(b <= t) fail = true;
 				if(COUNT) {   // counters keep the reference's side geometry (384 rows per 128-byte side)
-					uint64_t sT; uint32_t offT; row_locus(w.top, sT, offT);
-					const bool same_side = !range || (w.bot - w.top) < (uint64_t)(384 - offT);
-					cx.c_lf += range ? 2 : 1; cx.c_sides += same_side ? 1 : 2;
+					uint64_t sT; uint32_t offT; row_locus(top, sT, offT);
+					const bool same_side = !range || (bot - top) < (uint64_t)(384 - offT);
+					c_lf += range ? 2 : 1; c_sides += same_side ? 1 : 2;
 				}
 			}
-			if(fail) cx.hit_and_restart(w);
-			else {
-				w.top = t; w.bot = b; w.dep++;
-				if(w.dep >= w.rlen) cx.hit_and_restart(w);
-			}
+			if(fail) hit_and_restart();
+			else { top = t; bot = b; dep++; if(dep >= rlen) hit_and_restart(); }
 		}
 	}
 	if(COUNT && a.ctr) {
-		atomicAdd(&a.ctr->partial_searches, cx.c_ps); atomicAdd(&a.ctr->ftab_probes, cx.c_ft);
-		atomicAdd(&a.ctr->sides_search, cx.c_sides); atomicAdd(&a.ctr->lf_steps, cx.c_lf);
+		atomicAdd(&a.ctr->partial_searches, c_ps); atomicAdd(&a.ctr->ftab_probes, c_ft);
+		atomicAdd(&a.ctr->sides_search, c_sides); atomicAdd(&a.ctr->lf_steps, c_lf);
 	}
 }
 
 typedef void (*SearchKernel)(const SearchArgs);
+// g: lanes per walk (2,4,8 = cooperative kernels on the sides; 16 = their G=1 instantiation);
+// 1 / 100 = thread-per-walk kernels with the read in 4 / 10 register words
 static SearchKernel search_kernel(int g, bool count) {
 	switch(g) {
-		case 1: {
-			static int mb = -1;
-			if(mb < 0) { const char* e = getenv("CFB_MINB"); mb = e ? atoi(e) : 5; }
-			if(count) return k_search_t<true, 4>;
-			switch(mb) { case 4: return k_search_t<false, 4>; case 6: return k_search_t<false, 6>; case 8: return k_search_t<false, 8>; default: return k_search_t<false, 5>; }
-		}
+		case 1: return count ? k_search_t<true, 4> : k_search_t<false, 4>;      // reads up to 128 bases
+		case 100: return count ? k_search_t<true, 10> : k_search_t<false, 10>;  // reads up to 320 bases
 		case 16: return count ? k_search<true, 1> : k_search<false, 1>;   // generic template at G = 1 (A/B only)
 		case 2: return count ? k_search<true, 2> : k_search<false, 2>;
 		case 4: return count ? k_search<true, 4> : k_search<false, 4>;
@@ -900,6 +1042,70 @@ __global__ void __launch_bounds__(kSearchThreads, 8) k_resolve_t(const ResolveAr
 	if(COUNT && a.ctr) { atomicAdd(&a.ctr->walk_steps, c_walk); atomicAdd(&a.ctr->rows_resolved, c_rows); }
 }
 
+// ---------------------------------------------------------------------------------------
+// k_resolve_c: 4 lanes per SA row over rank16.  Lane j fetches the entry of base j, so the 64-byte
+// chunk of a block arrives with ONE load request per walk step; the lane whose indicator bit is set
+// at the row knows BWT[row] and its own LF value is the next row.  The genome-boundary prefilter is the
+// flag bit in A's occ word (no separate bitmap load).
+// ---------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kSearchThreads) k_resolve_c(const ResolveArgs a) {
+	const unsigned lane = threadIdx.x & 31, gl = lane & 3, gbase = lane & 28, gmask = 0xFu << gbase;
+	const ulonglong2* r16 = reinterpret_cast<const ulonglong2*>(a.v.rank16);
+	uint64_t n = *a.total; if(n > a.rows_cap) n = a.rows_cap;
+	const uint64_t lowmask = ((uint64_t)1 << a.v.off_rate) - 1;
+	uint64_t idx = 0, row = 0;
+	int mode = R_NEED;
+	unsigned long long c_walk = 0, c_rows = 0;
+	WarpPool pool; pool.base = pool.end = 0;
+	bool more = true;
+	auto settle = [&](uint64_t r) -> int {
+		if(r == a.v.zoff) { if(gl == 0) a.ids[idx] = 0; return R_NEED; }
+		if((r & lowmask) == 0) return R_SAMPLE;
+		return R_WALK;
+	};
+	for(;;) {
+		{
+			const bool want = mode == R_NEED;
+			if(more) {
+				unsigned long long t = 0;
+				bool got = pool_take(pool, want && gl == 0, a.task_ctr, (unsigned long long)n, a.chunk, t);
+				t = __shfl_sync(0xffffffffu, t, gbase); got = __shfl_sync(0xffffffffu, (int)got, gbase) != 0;
+				if(want) {
+					if(got) { idx = t; row = a.rows[idx]; if(COUNT && gl == 0) c_rows++; mode = settle(row); }
+					else mode = R_DONE;
+				}
+				if(__any_sync(0xffffffffu, want && !got)) more = false;
+			} else if(want) mode = R_DONE;
+		}
+		if(!__any_sync(0xffffffffu, mode != R_DONE)) break;
+		ulonglong2 e = make_ulonglong2(0, 0); uint32_t samp = 0;
+		if(mode == R_WALK) e = __ldg(r16 + (row >> 6) * 4 + gl);
+		else if(mode == R_SAMPLE && gl == 0) samp = a.v.sample32 ? __ldg(a.v.sample32 + (row >> a.v.off_rate)) : (uint32_t)__ldg(a.v.sample16 + (row >> a.v.off_rate));
+		if(mode == R_SAMPLE) { if(gl == 0) a.ids[idx] = samp; mode = R_NEED; }
+		else if(mode == R_WALK) {
+			const uint32_t off = (uint32_t)(row & 63);
+			const unsigned flagged = __shfl_sync(gmask, (unsigned)(e.x >> 63), gbase);     // A's entry carries the boundary flag
+			bool found = false;
+			if(flagged && a.v.last_boundary > 0 && row <= a.v.last_boundary) {
+				uint32_t lo = 0, hi = a.v.n_boundaries;
+				while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(a.v.brow[mid] < row) lo = mid + 1; else hi = mid; }
+				if(lo < a.v.n_boundaries && a.v.brow[lo] == row) { found = true; if(gl == 0) a.ids[idx] = a.v.sample32 ? a.v.bseq[lo] : (uint32_t)(uint16_t)a.v.bseq[lo]; }
+			}
+			if(found) mode = R_NEED;
+			else {
+				const uint64_t mine = a.v.fchr[gl] + (e.x & kOccMask) + (uint64_t)__popcll(e.y & ((1ull << off) - 1ull));
+				const unsigned who = (__ballot_sync(gmask, (e.y >> off) & 1ull) >> gbase) & 0xFu;      // exactly one base owns the row
+				const int src = __ffs(who) - 1;
+				row = __shfl_sync(gmask, mine, gbase + (src < 0 ? 0 : src));
+				if(COUNT && gl == 0) c_walk++;
+				mode = settle(row);
+			}
+		}
+	}
+	if(COUNT && gl == 0 && a.ctr) { atomicAdd(&a.ctr->walk_steps, c_walk); atomicAdd(&a.ctr->rows_resolved, c_rows); }
+}
+
 // =======================================================================================
 // k_compact
 // =======================================================================================
@@ -1045,6 +1251,32 @@ extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out)
 			CK(cudaDeviceSynchronize());
 			v.rankv = rv;
 		}
+		{   // 16-byte rank entries + fused ftab for the walk kernels
+			uint64_t* r16 = nullptr; const uint64_t nb = h.num_sides * 6;
+			CK(cudaMalloc((void**)&r16, (nb + 1) * 64));
+			ix->dptrs.push_back(r16); ix->device_bytes += (nb + 1) * 64;
+			k_build_rank16<<<(unsigned)((nb + 1 + 255) / 256), 256>>>(v.sides, h.num_sides, v.zside, v.zoffc, r16);
+			if(v.n_boundaries) k_mark_boundaries<<<(v.n_boundaries + 255) / 256, 256>>>(v.brow, v.n_boundaries, r16);
+			uint64_t* f2 = nullptr; const uint64_t nf = h.ftab_len - 1;
+			CK(cudaMalloc((void**)&f2, nf * 16));
+			ix->dptrs.push_back(f2); ix->device_bytes += nf * 16;
+			k_build_ftab2<<<(unsigned)((nf + 255) / 256), 256>>>(v, nf, f2);
+			CK(cudaDeviceSynchronize());
+			v.rank16 = r16; v.ftab2 = f2;
+			// extended jump table: K = largest value with 4^K <= len/4 (most K-mers occur), capped at 15 and by free HBM
+			int K = 0;
+			{ const char* e = getenv("CFB_FTABK"); if(e) K = atoi(e); else { K = h.ftab_chars; while(K < 15 && (4ull << (2 * K)) <= h.len / 4) K++; } }
+			size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+			while(K > h.ftab_chars && (16ull << (2 * K)) > free_b / 3) K--;
+			if(K > h.ftab_chars && K <= 16) {
+				uint64_t* fk = nullptr; const uint64_t nk = 1ull << (2 * K);
+				CK(cudaMalloc((void**)&fk, nk * 16));
+				ix->dptrs.push_back(fk); ix->device_bytes += nk * 16;
+				k_build_ftabk<<<(unsigned)((nk + 255) / 256), 256>>>(v, K, nk, fk);
+				CK(cudaDeviceSynchronize());
+				v.ftabk = fk; v.ftabk_chars = K;
+			}
+		}
 		// host copies of the big arrays are no longer needed once uploaded
 		std::vector<uint8_t>().swap(ix->h.sides);
 	}
@@ -1122,7 +1354,7 @@ struct cfb_ctx {
 	Slot slots[kSlots];
 	Counters* d_ctr = nullptr; bool count = false;
 	uint64_t launches = 0;
-	int search_blocks = 0, resolve_blocks = 0, group = 1; bool resolve_t = true;
+	int search_blocks = 0, resolve_blocks = 0, group = 1; int resolve_mode = 2;   // 0 = 8-lane sides, 1 = thread/blocks, 2 = 4-lane rank16
 	cfb_dbatch resident; bool resident_used = false;
 };
 
@@ -1187,12 +1419,28 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 		CKC(c->slots[i].scal.ensure(8)); CKC(c->slots[i].h_scal.ensure(8));
 	}
 	CKC(cudaMalloc((void**)&c->d_ctr, sizeof(Counters))); CKC(cudaMemset(c->d_ctr, 0, sizeof(Counters)));
+	{   // random 32-byte sector gathers: do not let L2 over-fetch neighbouring sectors from HBM
+		const char* e = getenv("CFB_L2_FETCH"); const size_t g = e ? (size_t)atoi(e) : 32;
+		if(g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+		const char* pe = getenv("CFB_L2_PERSIST");
+		if(pe && pe[0] == '1') {   // keep the 8.4 MB ftab resident in L2 (hit by every partial search)
+			cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 16u << 20);
+			for(int i = 0; i < kSlots; i++) {
+				cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+				av.accessPolicyWindow.base_ptr = (void*)c->view.ftab; av.accessPolicyWindow.num_bytes = h.ftab.size() * 8;
+				av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+				cudaStreamSetAttribute(c->slots[i].st, cudaStreamAttributeAccessPolicyWindow, &av);
+			}
+		}
+		cudaGetLastError();
+	}
 	int occ = 0;
 	{ const char* g = getenv("CFB_GROUP"); if(g) { const int v = atoi(g); if(v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->group = v; } }
 	CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel(c->group, false), kSearchThreads, 0));
 	c->search_blocks = ix->sm_count * std::max(occ, 1);
-	{ const char* g = getenv("CFB_RESOLVE_COOP"); if(g && g[0] == '1') c->resolve_t = false; }
-	if(c->resolve_t) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_t<false>, kSearchThreads, 0));
+	{ const char* g = getenv("CFB_RESOLVE"); if(g) c->resolve_mode = atoi(g); }
+	if(c->resolve_mode == 2) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_c<false>, kSearchThreads, 0));
+	else if(c->resolve_mode == 1) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_t<false>, kSearchThreads, 0));
 	else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
 	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
 	const char* cnt = getenv("CFB_COUNT");
@@ -1277,15 +1525,22 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 		{ PackArgs pa; pa.b = s.bv; pa.pk = s.pk.p; pa.nm = s.nm.p; pa.W = W;
 		  k_pack<<<(unsigned)((ntasks * W + 127) / 128), 128, 0, s.st>>>(pa); c->launches++; }
 		sa.task_ctr = (unsigned int*)(s.scal.p + 0); sa.task_ctr64 = s.scal.p + 0; sa.ntasks = (uint32_t)ntasks; sa.overflow = (unsigned int*)(s.scal.p + 2); sa.ctr = ctr;
-		const uint64_t per_block = kSearchThreads / (c->group == 16 ? 1 : c->group);
-		const uint64_t groups = (uint64_t)c->search_blocks * per_block;
+		int variant = c->group;
+		if(variant == 1) { if(s.maxlen > 320) variant = 16; else if(s.maxlen > 128) variant = 100; }   // longer reads: wider register window / windowed kernel
+		const bool pooled = variant == 1 || variant == 100;
+		const int lanes = (variant == 16 || pooled) ? 1 : variant;
+		int occ = 1;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel(variant, c->count), kSearchThreads, 0));
+		const uint64_t resident = (uint64_t)c->ix->sm_count * (uint64_t)std::max(occ, 1);
+		const uint64_t per_block = kSearchThreads / lanes;
+		const uint64_t groups = resident * per_block;
 		uint64_t chunk = ntasks / (groups * 8); sa.chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(chunk, 1), 16);
-		if(c->group == 1) {   // pooled hand-out: one atomic per warp refill of >= 32 tasks
-			const uint64_t warps = (uint64_t)c->search_blocks * (kSearchThreads / 32);
+		if(pooled) {   // one atomic per warp refill of >= 32 tasks
+			const uint64_t warps = resident * (kSearchThreads / 32);
 			sa.chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ntasks / (warps * 4), 32), 256);
 		}
-		const int blocks = (int)std::min<uint64_t>((uint64_t)c->search_blocks, (ntasks + per_block - 1) / per_block);
-		search_kernel(c->group, c->count)<<<blocks, kSearchThreads, 0, s.st>>>(sa);
+		const int blocks = (int)std::min<uint64_t>(resident, (ntasks + per_block - 1) / per_block);
+		search_kernel(variant, c->count)<<<blocks, kSearchThreads, 0, s.st>>>(sa);
 		c->launches++;
 		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
 		k_prep<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
@@ -1297,8 +1552,9 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	k_rows<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
 	if(time_it) CK(cudaEventRecord(s.ev[2], s.st));
 	ResolveArgs ra; ra.v = c->view; ra.rows = s.rows.p; ra.ids = s.ids.p; ra.total = (const uint64_t*)(s.scal.p + 3); ra.rows_cap = s.rows_cap;
-	ra.task_ctr = s.scal.p + 1; ra.chunk = c->resolve_t ? 128 : 4; ra.ctr = ctr;
-	if(c->resolve_t) { if(c->count) k_resolve_t<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve_t<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
+	ra.task_ctr = s.scal.p + 1; ra.chunk = c->resolve_mode == 2 ? 64 : (c->resolve_mode == 1 ? 128 : 4); ra.ctr = ctr;
+	if(c->resolve_mode == 2) { if(c->count) k_resolve_c<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve_c<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
+	else if(c->resolve_mode == 1) { if(c->count) k_resolve_t<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve_t<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
 	else { if(c->count) k_resolve<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
 	c->launches++;
 	if(time_it) CK(cudaEventRecord(s.ev[3], s.st));
