@@ -49,6 +49,8 @@ struct IndexView {
 	const uint64_t* rankv;          // device-only per-base rank sectors: 32 bytes per (192 rows, base)
 	const uint64_t* rank16;         // device-only rank entries: 16 bytes (occ_c, 64 indicator bits) per (64 rows, base)
 	const uint64_t* ftab2;          // device-only fused ftab: (top, bot) per 10-mer, eftab already resolved
+	const uint16_t* rtab16;         // device-only resolve table: sequence id of EVERY SA row (one of rtab16/rtab32, or neither)
+	const uint32_t* rtab32;
 	const uint64_t* ftabk;          // device-only extended jump table: (top, bot) per K-mer, K = ftabk_chars (0 = absent)
 	uint64_t len, zoff, zside, fchr[4], last_boundary, num_sides, num_blocks;
 	uint32_t zoffc, n_boundaries, n_seqs, n_host;

@@ -888,7 +888,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_apply(const uint32_t* in, u
 // =======================================================================================
 enum { R_DONE = 0, R_WALK = 1, R_SAMPLE = 2, R_NEED = 3 };
 struct ResolveArgs {
-	IndexView v; const uint64_t* rows; uint32_t* ids; const uint64_t* total; uint64_t rows_cap;
+	IndexView v; const uint64_t* rows; uint32_t* ids; uint16_t* ids16; const uint64_t* total; uint64_t rows_cap;
 	unsigned long long* task_ctr; uint32_t chunk; Counters* ctr;
 };
 
@@ -1048,7 +1048,8 @@ __global__ void __launch_bounds__(kSearchThreads, 8) k_resolve_t(const ResolveAr
 // at the row knows BWT[row] and its own LF value is the next row.  The genome-boundary prefilter is the
 // flag bit in A's occ word (no separate bitmap load).
 // ---------------------------------------------------------------------------------------
-template <bool COUNT>
+// IDENT: rows are 0..n-1 themselves and results go to the (16- or 32-bit) resolve table -- used once at index load
+template <bool COUNT, bool IDENT>
 __global__ void __launch_bounds__(kSearchThreads) k_resolve_c(const ResolveArgs a) {
 	const unsigned lane = threadIdx.x & 31, gl = lane & 3, gbase = lane & 28, gmask = 0xFu << gbase;
 	const ulonglong2* r16 = reinterpret_cast<const ulonglong2*>(a.v.rank16);
@@ -1059,8 +1060,9 @@ __global__ void __launch_bounds__(kSearchThreads) k_resolve_c(const ResolveArgs 
 	unsigned long long c_walk = 0, c_rows = 0;
 	WarpPool pool; pool.base = pool.end = 0;
 	bool more = true;
+	auto put = [&](uint32_t v) { if(IDENT && a.ids16) a.ids16[idx] = (uint16_t)v; else a.ids[idx] = v; };
 	auto settle = [&](uint64_t r) -> int {
-		if(r == a.v.zoff) { if(gl == 0) a.ids[idx] = 0; return R_NEED; }
+		if(r == a.v.zoff) { if(gl == 0) put(0); return R_NEED; }
 		if((r & lowmask) == 0) return R_SAMPLE;
 		return R_WALK;
 	};
@@ -1072,7 +1074,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_resolve_c(const ResolveArgs 
 				bool got = pool_take(pool, want && gl == 0, a.task_ctr, (unsigned long long)n, a.chunk, t);
 				t = __shfl_sync(0xffffffffu, t, gbase); got = __shfl_sync(0xffffffffu, (int)got, gbase) != 0;
 				if(want) {
-					if(got) { idx = t; row = a.rows[idx]; if(COUNT && gl == 0) c_rows++; mode = settle(row); }
+					if(got) { idx = t; row = IDENT ? idx : a.rows[idx]; if(COUNT && gl == 0) c_rows++; mode = settle(row); }
 					else mode = R_DONE;
 				}
 				if(__any_sync(0xffffffffu, want && !got)) more = false;
@@ -1082,7 +1084,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_resolve_c(const ResolveArgs 
 		ulonglong2 e = make_ulonglong2(0, 0); uint32_t samp = 0;
 		if(mode == R_WALK) e = __ldg(r16 + (row >> 6) * 4 + gl);
 		else if(mode == R_SAMPLE && gl == 0) samp = a.v.sample32 ? __ldg(a.v.sample32 + (row >> a.v.off_rate)) : (uint32_t)__ldg(a.v.sample16 + (row >> a.v.off_rate));
-		if(mode == R_SAMPLE) { if(gl == 0) a.ids[idx] = samp; mode = R_NEED; }
+		if(mode == R_SAMPLE) { if(gl == 0) put(samp); mode = R_NEED; }
 		else if(mode == R_WALK) {
 			const uint32_t off = (uint32_t)(row & 63);
 			const unsigned flagged = __shfl_sync(gmask, (unsigned)(e.x >> 63), gbase);     // A's entry carries the boundary flag
@@ -1090,7 +1092,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_resolve_c(const ResolveArgs 
 			if(flagged && a.v.last_boundary > 0 && row <= a.v.last_boundary) {
 				uint32_t lo = 0, hi = a.v.n_boundaries;
 				while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(a.v.brow[mid] < row) lo = mid + 1; else hi = mid; }
-				if(lo < a.v.n_boundaries && a.v.brow[lo] == row) { found = true; if(gl == 0) a.ids[idx] = a.v.sample32 ? a.v.bseq[lo] : (uint32_t)(uint16_t)a.v.bseq[lo]; }
+				if(lo < a.v.n_boundaries && a.v.brow[lo] == row) { found = true; if(gl == 0) put(a.v.sample32 ? a.v.bseq[lo] : (uint32_t)(uint16_t)a.v.bseq[lo]); }
 			}
 			if(found) mode = R_NEED;
 			else {
@@ -1104,6 +1106,15 @@ __global__ void __launch_bounds__(kSearchThreads) k_resolve_c(const ResolveArgs 
 		}
 	}
 	if(COUNT && gl == 0 && a.ctr) { atomicAdd(&a.ctr->walk_steps, c_walk); atomicAdd(&a.ctr->rows_resolved, c_rows); }
+}
+
+// Resolve by table: the sequence id of every SA row was precomputed at index load (k_resolve_c<.,true>), so
+// resolving a row is one 2- or 4-byte gather instead of a ~8-step dependent walk.
+__global__ void __launch_bounds__(256) k_lookup(const ResolveArgs a) {
+	uint64_t n = *a.total; if(n > a.rows_cap) n = a.rows_cap;
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for(uint64_t k = i; k < n; k += stride) { const uint64_t r = a.rows[k]; a.ids[k] = a.v.rtab32 ? __ldg(a.v.rtab32 + r) : (uint32_t)__ldg(a.v.rtab16 + r); }
 }
 
 // =======================================================================================
@@ -1235,7 +1246,7 @@ extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out)
 		v.last_boundary = h.last_boundary; v.num_sides = h.num_sides;
 		v.n_boundaries = (uint32_t)h.brow.size(); v.n_seqs = (uint32_t)h.seq_taxid.size();
 		v.off_rate = h.off_rate; v.ftab_chars = h.ftab_chars; v.bshift = h.bshift;
-		{   // re-blocked replica for the thread-per-walk kernels
+		if(getenv("CFB_LEGACY_LAYOUTS")) {   // 64-byte blocks: only for the k_resolve_t A/B variant (CFB_RESOLVE=1)
 			uint64_t* blk = nullptr; const uint64_t nb = h.num_sides * 3;
 			CK(cudaMalloc((void**)&blk, (nb + 1) * 64));
 			ix->dptrs.push_back(blk); ix->device_bytes += (nb + 1) * 64;
@@ -1243,7 +1254,7 @@ extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out)
 			CK(cudaDeviceSynchronize());
 			v.blocks = blk; v.num_blocks = nb;
 		}
-		{   // per-base rank sectors for the search kernel
+		if(getenv("CFB_LEGACY_LAYOUTS")) {   // 32-byte rank sectors: superseded by rank16, kept for A/B only
 			uint64_t* rv = nullptr; const uint64_t nb = h.num_sides * 2;
 			CK(cudaMalloc((void**)&rv, (nb + 1) * 128));
 			ix->dptrs.push_back(rv); ix->device_bytes += (nb + 1) * 128;
@@ -1275,6 +1286,26 @@ extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out)
 				k_build_ftabk<<<(unsigned)((nk + 255) / 256), 256>>>(v, K, nk, fk);
 				CK(cudaDeviceSynchronize());
 				v.ftabk = fk; v.ftabk_chars = K;
+			}
+			// resolve table: sequence id of every SA row (walked once here), if it fits comfortably
+			{
+				const char* e = getenv("CFB_RESOLVE_TABLE");
+				const uint64_t nrows = h.len + 1, esz = h.wide_sample ? 4 : 2;
+				cudaMemGetInfo(&free_b, &total_b);
+				if(!(e && e[0] == '0') && nrows * esz < free_b / 3) {
+					void* tab = nullptr; unsigned long long* sc = nullptr;
+					CK(cudaMalloc(&tab, nrows * esz + 16)); CK(cudaMalloc((void**)&sc, 16));
+					ix->dptrs.push_back(tab); ix->device_bytes += nrows * esz;
+					const unsigned long long init[2] = {0ull, (unsigned long long)nrows};
+					CK(cudaMemcpy(sc, init, 16, cudaMemcpyHostToDevice));
+					ResolveArgs ra; ra.v = v; ra.rows = nullptr; ra.ids = h.wide_sample ? (uint32_t*)tab : nullptr; ra.ids16 = h.wide_sample ? nullptr : (uint16_t*)tab;
+					ra.total = (const uint64_t*)(sc + 1); ra.rows_cap = nrows; ra.task_ctr = sc; ra.chunk = 256; ra.ctr = nullptr;
+					int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_c<false, true>, kSearchThreads, 0);
+					k_resolve_c<false, true><<<prop.multiProcessorCount * std::max(occ, 1), kSearchThreads>>>(ra);
+					CK(cudaDeviceSynchronize());
+					cudaFree(sc);
+					if(h.wide_sample) v.rtab32 = (const uint32_t*)tab; else v.rtab16 = (const uint16_t*)tab;
+				}
 			}
 		}
 		// host copies of the big arrays are no longer needed once uploaded
@@ -1438,8 +1469,10 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 	{ const char* g = getenv("CFB_GROUP"); if(g) { const int v = atoi(g); if(v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->group = v; } }
 	CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel(c->group, false), kSearchThreads, 0));
 	c->search_blocks = ix->sm_count * std::max(occ, 1);
-	{ const char* g = getenv("CFB_RESOLVE"); if(g) c->resolve_mode = atoi(g); }
-	if(c->resolve_mode == 2) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_c<false>, kSearchThreads, 0));
+	{ const char* g = getenv("CFB_RESOLVE"); if(g) c->resolve_mode = atoi(g); else if(c->view.rtab16 || c->view.rtab32) c->resolve_mode = 3; }
+	if(c->resolve_mode == 3 && !(c->view.rtab16 || c->view.rtab32)) c->resolve_mode = 2;
+	if(c->resolve_mode == 1 && !c->view.blocks) c->resolve_mode = 2;
+	if(c->resolve_mode >= 2) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_c<false, false>, kSearchThreads, 0));
 	else if(c->resolve_mode == 1) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_t<false>, kSearchThreads, 0));
 	else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
 	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
@@ -1551,9 +1584,10 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	} else if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
 	k_rows<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
 	if(time_it) CK(cudaEventRecord(s.ev[2], s.st));
-	ResolveArgs ra; ra.v = c->view; ra.rows = s.rows.p; ra.ids = s.ids.p; ra.total = (const uint64_t*)(s.scal.p + 3); ra.rows_cap = s.rows_cap;
-	ra.task_ctr = s.scal.p + 1; ra.chunk = c->resolve_mode == 2 ? 64 : (c->resolve_mode == 1 ? 128 : 4); ra.ctr = ctr;
-	if(c->resolve_mode == 2) { if(c->count) k_resolve_c<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve_c<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
+	ResolveArgs ra; ra.v = c->view; ra.rows = s.rows.p; ra.ids = s.ids.p; ra.ids16 = nullptr; ra.total = (const uint64_t*)(s.scal.p + 3); ra.rows_cap = s.rows_cap;
+	ra.task_ctr = s.scal.p + 1; ra.chunk = c->resolve_mode >= 2 ? 64 : (c->resolve_mode == 1 ? 128 : 4); ra.ctr = ctr;
+	if(c->resolve_mode == 3 && !c->count) k_lookup<<<c->ix->sm_count * 8, 256, 0, s.st>>>(ra);
+	else if(c->resolve_mode >= 2) { if(c->count) k_resolve_c<true, false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve_c<false, false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
 	else if(c->resolve_mode == 1) { if(c->count) k_resolve_t<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve_t<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
 	else { if(c->count) k_resolve<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
 	c->launches++;
@@ -1692,7 +1726,7 @@ extern "C" int cfb_test_resolve(const cfb_index* ix, const uint64_t* rows, uint6
 	CK(cudaMemcpy(dr, rows, n * 8, cudaMemcpyHostToDevice));
 	unsigned long long init[2] = {0ull, (unsigned long long)n};
 	CK(cudaMemcpy(sc, init, 16, cudaMemcpyHostToDevice));
-	ResolveArgs ra; ra.v = ix->view; ra.rows = dr; ra.ids = dout; ra.total = (const uint64_t*)(sc + 1); ra.rows_cap = n; ra.task_ctr = sc; ra.chunk = 2; ra.ctr = nullptr;
+	ResolveArgs ra; ra.v = ix->view; ra.rows = dr; ra.ids = dout; ra.ids16 = nullptr; ra.total = (const uint64_t*)(sc + 1); ra.rows_cap = n; ra.task_ctr = sc; ra.chunk = 2; ra.ctr = nullptr;
 	k_resolve<false><<<32, kSearchThreads>>>(ra);
 	CK(cudaDeviceSynchronize());
 	CK(cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost));
