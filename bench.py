@@ -5,8 +5,8 @@ A "step" is one pass of the hot path over one batch of synthetic 100 bp single-e
 synthetic genus/species index (SURVEY.md Appendix C recipe) replicated in each GPU's HBM.
 
   value     reads/s with the batch already resident in HBM (kernels only, CUDA events, max over ranks)
-  e2e       reads/s through cfb_classify_submit/wait with HOST buffers: H2D of the packed reads and
-            D2H of the result records inside the timed region
+  e2e       reads/s through cfb_classify_submit/wait with HOST buffers: H2D of the reads and D2H of the
+            result records inside the timed region, up to cfb_ctx_slots() batches in flight
   roofline  k_search: algorithmic bytes (128 B per side touched + 16 B per ftab probe, counted by the
             kernel's own counters in a separate un-timed pass) / its CUDA-event time, vs measured HBM peak
   cpu_baseline   the unmodified reference binary (oracle/_ref/centrifuge-class -p <cores>) on a bounded sample
@@ -168,6 +168,19 @@ def measured_peak():
 
 # ------------------------------------------------------------------------------------ main
 def main():
+    # stdout carries exactly one JSON line: route everything else that native libraries print to fd 1
+    # (e.g. NCCL's version banner) to stderr, and keep a private handle for the result line
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+    result = os.fdopen(result_fd, "w")
+    try:
+        return _main(result)
+    finally:
+        result.flush()
+
+
+def _main(result):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -204,7 +217,7 @@ def main():
                           "dtype": "u64", "data": "synthetic", "impl": "reference",
                           "config": {"workload": workload, "sample": sample},
                           "cpu_baseline": {"value": val, "unit": "reads/s", "cores": arm.threads, "kind": "reference", "sample": sample},
-                          "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=result, flush=True)
         return 0
 
     import torch
@@ -288,8 +301,11 @@ def main():
 
     # ---------------- e2e: host buffers in, host records out, 2 batches in flight
     nslots = ctx.n_slots
-    for _ in range(min(a.warmup, 2)):
-        ctx.submit(0, batch); ctx.wait(0, copy=False)
+    for _ in range(max(1, min(a.warmup, 2))):          # every slot allocates its buffers before the timed region
+        for sl in range(nslots):
+            ctx.submit(sl, batch)
+        for sl in range(nslots):
+            ctx.wait(sl, copy=False)
     sync_all()
     t0 = time.perf_counter()
     inflight = []
@@ -341,7 +357,7 @@ def main():
                                    "sample": "%d reads, centrifuge-class -p %d (best of a sweep up to %d threads), FASTQ in, TSV to /dev/null, index load differenced out" % (nn, arm.threads, ncores)}
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": ncores, "kind": "reference", "sample": "failed: %s" % e}
-        print(json.dumps(out))
+        print(json.dumps(out), file=result, flush=True)
     ctx.close(); ix.close()
     if dist:
         dist.destroy_process_group()

@@ -1348,7 +1348,7 @@ extern "C" void cfb_params_default(cfb_params* p) {
 }
 
 // ---------------------------------------------------------------------------------------
-static const int kSlots = 3;
+static const int kSlots = 5;   // 4 pipelined slots + 1 for resident batches
 
 struct Slot {
 	cudaStream_t st = nullptr;
