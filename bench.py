@@ -299,33 +299,41 @@ def _main(result):
     dev_s, wall_s = float(t_dev[0]), float(t_dev[1])
     value = world * n * a.steps / dev_s
 
-    # ---------------- e2e: host buffers in, host records out, 2 batches in flight
+    # ---------------- e2e: host buffers in, host records out.  One step = the same batch, cut into
+    # n_slots sub-batches that are submitted back to back (H2D of one overlaps the kernels of another)
+    # and then waited for: every step is self-contained, all copies are inside the timed region.
     nslots = ctx.n_slots
+    m = n // nslots
+    sub = []
+    offs_sub = capi.pinned_array((m,), np.uint64); offs_sub[:] = np.arange(m, dtype=np.uint64) * np.uint64(a.rdlen)
+    for sl in range(nslots):
+        sub.append(capi.make_batch(bases[sl * m * a.rdlen:(sl + 1) * m * a.rdlen], offs_sub, lens[sl * m:(sl + 1) * m], None, None, flags[sl * m:(sl + 1) * m]))
+    n_e2e = m * nslots
+
+    def e2e_step():
+        nr = 0
+        for sl in range(nslots):
+            ctx.submit(sl, sub[sl])
+        for sl in range(nslots):
+            nr += ctx.wait(sl, copy=False)[1]
+        return nr
+
     for _ in range(max(1, min(a.warmup, 2))):          # every slot allocates its buffers before the timed region
-        for sl in range(nslots):
-            ctx.submit(sl, batch)
-        for sl in range(nslots):
-            ctx.wait(sl, copy=False)
+        e2e_step()
     sync_all()
     t0 = time.perf_counter()
-    inflight = []
     d2h = 0
     for s in range(a.steps):
-        slot = s % nslots
-        if len(inflight) == nslots:
-            _, nr = ctx.wait(inflight.pop(0), copy=False); d2h += nr * 24 + (n + 1) * 4
-        ctx.submit(slot, batch); inflight.append(slot)
-    while inflight:
-        _, nr = ctx.wait(inflight.pop(0), copy=False); d2h += nr * 24 + (n + 1) * 4
-    if dist:
-        step_counts = counts.clone()
-        dist.all_reduce(step_counts)
+        d2h += e2e_step() * 24 + (n_e2e + nslots) * 4
+        if dist:
+            step_counts = counts.clone()
+            dist.all_reduce(step_counts)
     sync_all()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = world * n * a.steps / float(te[0])
+    e2e = world * n_e2e * a.steps / float(te[0])
     sampler.stop_flag = True; sampler.join(timeout=2)
     launches_total = ctx.launches()
     h2d = bases.nbytes + offs.nbytes + lens.nbytes + flags.nbytes
@@ -333,6 +341,16 @@ def _main(result):
     peak, peak_src = measured_peak()
     search_s = kms[0] / 1000.0 / a.steps
     achieved = bytes_search / search_s / 1e9
+    # measured DRAM traffic of the kernel (one ncu --set full capture, profiles/r01_traffic.json), scaled to this launch
+    traffic, gather = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_read"] * n
+        sect = tj["dram_bytes_read"] / 32.0 / tj["reads_in_capture"] * n          # 32-byte DRAM sectors read per launch
+        gather = {"what": "random 32-byte sector gathers: achieved vs the ceiling measured on this part by tools/gather_bench.cu (~34.5 G sectors/s)",
+                  "achieved_gsectors_s": sect / search_s / 1e9, "ceiling_gsectors_s": 34.5, "frac": sect / search_s / 1e9 / 34.5}
     out = {
         "metric": "reads/sec (100 bp SE classification)", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1000 * dev_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -340,7 +358,7 @@ def _main(result):
                    "parallelism": "reads sharded over %d GPU(s), index replicated, 1 NCCL all-reduce of per-taxon counts per step" % world},
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h // max(a.steps, 1))},
         "gpu_launches": int(launches_value),
-        "roofline": {"bound": "hbm", "kernel": "k_search_t", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "k_search_t", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "random_gather": gather,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_search), "kernel_ms": 1000 * search_s,
                      "sides_per_read": ctr["sides_search"] / max(ctr["units"], 1), "walk_bytes_per_launch": int(bytes_walk)},
         "kernel_ms": {"search": kms[0] / a.steps, "prep_rows": kms[1] / a.steps, "resolve": kms[2] / a.steps, "score_compact": kms[3] / a.steps, "total": step_ms},
