@@ -28,6 +28,16 @@
 #include <unordered_map>
 #include <vector>
 
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 using namespace cfb;
 
 // the loader's HostIndex lives inside cfb_index; the driver only needs these accessors
@@ -43,6 +53,8 @@ struct Options {
 	uint64_t skip = 0, upto = std::numeric_limits<uint64_t>::max();
 	uint32_t seed = 0;
 	size_t batch_units = 1u << 18;
+	size_t text_block = 64u << 20;      // bytes of read file per device span (text operator)
+	bool host_parse = false;            // force the host reader / formatter
 	cfb_params prm; std::vector<uint64_t> host, excl;
 	int trim5 = 0, trim3 = 0;
 };
@@ -52,7 +64,7 @@ static const OptDesc kLong[] = {
 	{"quiet", 0}, {"time", 0}, {"seed", 1}, {"upto", 1}, {"qupto", 1}, {"skip", 1}, {"version", 0}, {"help", 0}, {"threads", 1},
 	{"reorder", 0}, {"mm", 0}, {"wrapper", 1}, {"arg-desc", 0}, {"report-file", 1}, {"no-abundance", 0}, {"no-traverse", 0},
 	{"min-hitlen", 1}, {"host-taxids", 1}, {"exclude-taxids", 1}, {"classification-rank", 1}, {"trim5", 1}, {"trim3", 1},
-	{"device", 1}, {"batch-units", 1}, {NULL, 0}};
+	{"device", 1}, {"batch-units", 1}, {"text-block-mb", 1}, {"host-parse", 0}, {NULL, 0}};
 static const char* kShort = "fqtu:s:p:k:1:2:U:x:S:3:5:h";
 
 std::vector<std::string> split(const std::string& s, char d) {
@@ -65,6 +77,7 @@ std::vector<std::string> split(const std::string& s, char d) {
 struct FileIn {       // buffered byte source with one-byte peek
 	FILE* f = NULL; std::vector<unsigned char> buf; size_t pos = 0, end = 0;
 	bool open(const std::string& p) { f = p == "-" ? stdin : fopen(p.c_str(), "rb"); buf.resize(1 << 22); return f != NULL; }
+	bool seek(uint64_t off) { pos = end = 0; return f && f != stdin && fseeko(f, (off_t)off, SEEK_SET) == 0; }
 	void close() { if(f && f != stdin) fclose(f); f = NULL; }
 	inline bool fill() { if(!f) return false; end = fread(buf.data(), 1, buf.size(), f); pos = 0; return end > 0; }
 	inline int get() { if(pos == end && !fill()) return -1; return buf[pos++]; }
@@ -152,14 +165,26 @@ static bool parse_fastq(FileIn& in, Rec& r, uint64_t& count, bool& first, int tr
 	if(trim3 > 0) r.seq.resize(r.seq.size() > (size_t)trim3 ? r.seq.size() - trim3 : 0);
 	for(;;) { int d = in.get(); if(d < 0) break; if(d == '\n' || d == '\r') { while(in.peek() == '\n' || in.peek() == '\r') in.get(); break; } }
 	if(nread == 0) { if(in.peek() == '@') in.get(); count++; return true; }
-	size_t qn = 0; int qi = 0;
+	// qualities: pat.cpp:1042-1078 (phred33).  Everything from trim5 on is kept, then trim3 is cut off the end;
+	// the kept string must be as long as the read or one longer.
+	size_t qn = 0, kept = 0; int qi = 0;
 	for(;;) {
 		c = in.get();
+		if(c == ' ') {
+			std::cerr << "Error: Encountered one or more spaces while parsing the quality string for read " << r.name << ".  If this is a FASTQ file with integer (non-ASCII-encoded) qualities, try re-running with the --integer-quals option." << std::endl;
+			throw 1;
+		}
 		if(c < 0 || c == '\r' || c == '\n') break;
-		if(qi >= trim5 && qn < r.seq.size()) { r.qx ^= ((uint32_t)(c & 0xff) << ((qn & 3) << 3)); qn++; }
+		if(qi >= trim5) {
+			if((int)(signed char)c < 33) { std::cerr << "Saw ASCII character " << (int)(signed char)c << " but expected 33-based Phred qual." << std::endl; throw 1; }   // charToPhred33 qual.h:136-142
+			kept++;
+			if(qn < r.seq.size()) { r.qx ^= ((uint32_t)(c & 0xff) << ((qn & 3) << 3)); qn++; }
+		}
 		qi++;
 	}
-	if(qn < r.seq.size()) { std::cerr << "Error: Read " << r.name << " has more read characters than quality values." << std::endl; throw 1; }
+	kept = kept > (size_t)trim3 ? kept - trim3 : 0;
+	if(kept < r.seq.size()) { std::cerr << "Error: Read " << r.name << " has more read characters than quality values." << std::endl; throw 1; }
+	if(kept > r.seq.size() + 1) { std::cerr << "Error: Read " << r.name << " has more quality values than read characters." << std::endl; throw 1; }
 	while(in.peek() == '\n' || in.peek() == '\r') in.get();
 	in.get();                                              // '@' of the next record (or EOF)
 	if(r.name.empty()) { char b[32]; snprintf(b, sizeof b, "%llu", (unsigned long long)count); r.name = b; }
@@ -413,6 +438,213 @@ struct Formatter {
 	}
 };
 
+
+// ------------------------------------------------------------------------------ text operator driver
+// Well-formed FASTQ/FASTA goes to the device as raw bytes (cfb_text_submit): this thread only reads the
+// file into pinned memory, counts line ends to cut spans at record boundaries, and writes the rows that
+// come back.  Anything irregular is handed to the record-level reader below from the first byte of the
+// span that failed, so the output never depends on the path taken.
+__attribute__((target_clones("avx2", "default")))
+static size_t count_nl(const unsigned char* p, size_t n) { size_t c = 0; for(size_t i = 0; i < n; i++) c += p[i] == '\n'; return c; }
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct SpanFile {        // one input file of a source, consumed in spans that end at record boundaries
+	int fd = -1; uint64_t file_pos = 0, file_size = 0, span_start = 0; bool eof = false;
+	std::vector<unsigned char> carry;              // bytes after the previous cut
+	bool open(const std::string& p) {
+		fd = ::open(p.c_str(), O_RDONLY);
+		if(fd < 0) return false;
+		struct stat st; if(fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); fd = -1; return false; }
+		file_size = (uint64_t)st.st_size;
+		posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+		return true;
+	}
+	void close() { if(fd >= 0) ::close(fd); fd = -1; }
+	// fill buf (capacity cap) with carry + file bytes up to `want`; returns bytes in buf, line ends in *lines.
+	// The file part is read by `threads` preads in parallel, each counting the line ends of its piece.
+	size_t fill(unsigned char* buf, size_t cap, size_t want, size_t* lines, int threads) {
+		size_t n = carry.size();
+		if(n) memcpy(buf, carry.data(), n);
+		span_start = file_pos - n;
+		size_t nl = count_nl(buf, n);
+		const uint64_t remain = file_size - file_pos;
+		size_t take = n < want ? (size_t)std::min<uint64_t>(remain, std::min(want - n, cap - 1 - n)) : 0;
+		if(take) {
+			const int P = take >= (8u << 20) ? std::max(threads, 1) : 1;
+			std::vector<size_t> got(P, 0), cnt(P, 0);
+			auto piece = [&](int k) {
+				const size_t lo = take * k / P, hi = take * (k + 1) / P; size_t done = lo;
+				while(done < hi) { const ssize_t r = pread(fd, buf + n + done, hi - done, (off_t)(file_pos + done)); if(r <= 0) break; done += (size_t)r; }
+				got[k] = done - lo; cnt[k] = count_nl(buf + n + lo, done - lo);
+			};
+			std::vector<std::thread> th;
+			for(int k = 1; k < P; k++) th.emplace_back(piece, k);
+			piece(0);
+			for(size_t k = 0; k < th.size(); k++) th[k].join();
+			size_t ok = 0; bool shortfall = false;
+			for(int k = 0; k < P; k++) { const size_t lo = take * k / P, hi = take * (k + 1) / P; if(shortfall) break; ok += got[k]; nl += cnt[k]; if(got[k] != hi - lo) shortfall = true; }
+			if(shortfall) { nl = count_nl(buf, n + ok); }       // file shrank under us: keep the contiguous prefix
+			n += ok; file_pos += ok;
+			if(shortfall) file_size = file_pos;
+		}
+		if(file_pos >= file_size) eof = true;
+		if(eof && n > 0 && buf[n - 1] != '\n') { buf[n++] = '\n'; nl++; }    // last line without a line end
+		*lines = nl;
+		return n;
+	}
+	// keep the first `keep_lines` lines of buf[0..n): returns the cut, stores the rest as carry
+	size_t cut(const unsigned char* buf, size_t n, size_t lines, size_t keep_lines) {
+		size_t end = n;
+		for(size_t drop = lines - keep_lines + 1; drop > 0 && end > 0; drop--) {      // walk back over (lines - keep) line ends, land on the keep-th
+			const void* q = memrchr(buf, '\n', end);
+			if(!q) { end = 0; break; }
+			end = (size_t)((const unsigned char*)q - buf);
+		}
+		const size_t c = keep_lines == 0 ? 0 : end + 1;
+		carry.assign(buf + c, buf + n);
+		return c;
+	}
+};
+
+struct MultiKeyHash { size_t operator()(const std::string& k) const { uint64_t h = 1469598103934665603ull; for(size_t i = 0; i < k.size(); i++) { h ^= (unsigned char)k[i]; h *= 1099511628211ull; } return (size_t)h; } };
+typedef std::unordered_map<std::string, uint64_t, MultiKeyHash> MultiObs;
+
+struct TextStats { uint64_t spans = 0, units = 0, bytes_in = 0, bytes_out = 0, fallbacks = 0; double t_read = 0, t_gpu_wait = 0, t_write = 0, t_total = 0; };
+
+template <class T> struct Chan {        // small blocking queue between the pipeline threads
+	std::mutex mu; std::condition_variable cv; std::deque<T> q; bool closed = false;
+	void push(const T& v) { { std::lock_guard<std::mutex> l(mu); q.push_back(v); } cv.notify_all(); }
+	void close() { { std::lock_guard<std::mutex> l(mu); closed = true; } cv.notify_all(); }
+	bool pop(T& v) { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return !q.empty() || closed; }); if(q.empty()) return false; v = q.front(); q.pop_front(); return true; }
+};
+
+// Three threads per source: a reader that fills pinned buffers and cuts spans at record boundaries, this
+// thread submitting spans to the device and collecting them in order, and a writer for the rows.
+struct TextPipe {
+	cfb_ctx* ctx; const Options& o; FILE* fo; MultiObs& multi; TextStats& st;
+	int nslots = 0; size_t cap = 0; int read_threads = 4;
+	std::vector<unsigned char*> buf[2];
+	TextPipe(cfb_ctx* c, const Options& o_, FILE* f, MultiObs& m, TextStats& s) : ctx(c), o(o_), fo(f), multi(m), st(s) {
+		if(const char* e = getenv("CFB_READ_THREADS")) read_threads = std::max(1, atoi(e));
+	}
+	~TextPipe() { for(int m = 0; m < 2; m++) for(size_t i = 0; i < buf[m].size(); i++) cfb_host_free(buf[m][i]); }
+	bool init(bool paired) {
+		nslots = cfb_ctx_slots(ctx); cap = 2 * o.text_block + 4096;
+		for(int m = 0; m < (paired ? 2 : 1); m++) while((int)buf[m].size() < nslots) {
+			unsigned char* p = (unsigned char*)cfb_host_alloc(cap);
+			if(!p) return false;
+			buf[m].push_back(p);
+		}
+		return true;
+	}
+	struct Span { int slot; size_t bytes[2]; size_t rec; uint64_t start[2]; uint32_t hint; bool irregular; };
+	struct Rows { int slot; const char* tsv; uint64_t tsv_bytes; const uint64_t* multi; uint64_t n_multi; uint32_t stride; };
+
+	// Runs one source.  Returns 0 when it was consumed completely, 1 when the record-level reader has to
+	// continue from byte offsets off[0..1] after `done` records, -1 on error.
+	int run(const std::string& pa, const std::string* pb, uint64_t off[2], uint64_t& done) {
+		const bool paired = pb != NULL; const size_t L = o.fasta ? 2 : 4; const int nm = paired ? 2 : 1;
+		off[0] = off[1] = 0; done = 0;
+		SpanFile f[2];
+		if(!f[0].open(pa) || (paired && !f[1].open(*pb))) { f[0].close(); f[1].close(); return 1; }   // not a regular file: the stream reader handles it (and reports errors)
+		if(!init(paired)) { std::cerr << "Error: could not allocate pinned buffers" << std::endl; return -1; }
+		const double t_begin = now_s();
+		Chan<int> free_slots; Chan<Span> spans; Chan<Rows> rows;
+		for(int i = 0; i < nslots; i++) free_slots.push(i);
+		std::atomic<bool> stop(false);
+		double t_read = 0, t_write = 0;
+
+		std::thread reader([&] {
+			bool first = true;
+			for(;;) {
+				int s;
+				if(!free_slots.pop(s) || stop.load()) break;
+				const double t0 = now_s();
+				Span sp; memset(&sp, 0, sizeof sp); sp.slot = s;
+				size_t n[2] = {0, 0}, lines[2] = {0, 0};
+				for(int m = 0; m < nm; m++) n[m] = f[m].fill(buf[m][s], cap, o.text_block, &lines[m], read_threads);
+				if(n[0] == 0 && (!paired || n[1] == 0)) { t_read += now_s() - t0; break; }      // input exhausted
+				size_t rec = lines[0] / L;
+				bool irregular = f[0].eof && lines[0] % L != 0;
+				if(paired) { rec = std::min(rec, lines[1] / L); irregular |= f[1].eof && lines[1] % L != 0; }
+				if(rec == 0) irregular = true;                       // a record longer than a span, or mates running out of step
+				sp.start[0] = f[0].span_start; sp.start[1] = paired ? f[1].span_start : 0; sp.irregular = irregular; sp.rec = rec;
+				if(!irregular) {
+					for(int m = 0; m < nm; m++) sp.bytes[m] = f[m].cut(buf[m][s], n[m], lines[m], rec * L);
+					if(first) {     // longest line in the head of the file sizes the first pass
+						first = false; size_t longest = 0, ls = 0; const size_t lim = std::min<size_t>(sp.bytes[0], 1u << 16);
+						for(size_t i = 0; i < lim; i++) if(buf[0][s][i] == '\n') { longest = std::max(longest, i - ls); ls = i + 1; }
+						sp.hint = (uint32_t)std::min<size_t>(longest, 60000);
+					}
+				}
+				t_read += now_s() - t0;
+				spans.push(sp);
+				if(irregular) break;
+			}
+			spans.close();
+		});
+		std::thread writer([&] {
+			Rows r;
+			while(rows.pop(r)) {
+				const double t0 = now_s();
+				if(r.tsv_bytes) fwrite(r.tsv, 1, r.tsv_bytes, fo);
+				for(uint64_t i = 0; i < r.n_multi; i++) {
+					const uint64_t* rec = r.multi + i * r.stride;
+					multi[std::string((const char*)(rec + 1), (size_t)rec[0] * 8)] += 1;
+				}
+				t_write += now_s() - t0;
+				free_slots.push(r.slot);
+			}
+		});
+
+		cfb_text_opts to; memset(&to, 0, sizeof to);
+		to.fasta = o.fasta ? 1 : 0; to.trim5 = o.trim5; to.trim3 = o.trim3; to.seed = o.seed;
+		std::deque<Span> flight;          // submitted, oldest first
+		int rc = 0; bool fallback = false; double t_wait = 0;
+		auto collect_oldest = [&]() {
+			const Span sp = flight.front(); flight.pop_front();
+			cfb_text_result r;
+			const double t0 = now_s();
+			const int e = cfb_text_wait(ctx, sp.slot, fallback ? 1 : 0, &r);
+			t_wait += now_s() - t0;
+			if(e != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; rc = -1; fallback = true; stop.store(true); free_slots.push(sp.slot); return; }
+			if(fallback) { free_slots.push(sp.slot); return; }
+			if(r.irregular) { fallback = true; stop.store(true); off[0] = sp.start[0]; off[1] = sp.start[1]; st.fallbacks++; free_slots.push(sp.slot); return; }
+			done += r.n_units; st.spans++; st.units += r.n_units; st.bytes_out += r.tsv_bytes;
+			Rows w; w.slot = sp.slot; w.tsv = r.tsv; w.tsv_bytes = r.tsv_bytes; w.multi = r.multi; w.n_multi = r.n_multi; w.stride = r.multi_stride;
+			rows.push(w);
+		};
+		for(;;) {
+			Span sp;
+			if(fallback || !spans.pop(sp)) break;
+			if(sp.irregular) {
+				while(!flight.empty() && !fallback) collect_oldest();
+				if(!fallback) { fallback = true; off[0] = sp.start[0]; off[1] = sp.start[1]; st.fallbacks++; }
+				free_slots.push(sp.slot);
+				break;
+			}
+			if(sp.hint) to.maxlen_hint = sp.hint;
+			if(cfb_text_submit(ctx, sp.slot, buf[0][sp.slot], sp.bytes[0], paired ? buf[1][sp.slot] : NULL, sp.bytes[1], sp.rec, &to) != CFB_OK) {
+				std::cerr << "Error: " << cfb_last_error() << std::endl; rc = -1; fallback = true; stop.store(true); free_slots.push(sp.slot); break;
+			}
+			st.bytes_in += sp.bytes[0] + sp.bytes[1];
+			flight.push_back(sp);
+			// keep the device two spans deep; collect the oldest as soon as a third is queued
+			while((int)flight.size() > std::max(1, nslots - 2) && !fallback) collect_oldest();
+		}
+		while(!flight.empty()) collect_oldest();
+		stop.store(true); free_slots.close();
+		{ Span sp; while(spans.pop(sp)) {} }      // reader may have queued spans after the failing one: they are re-read by the record reader
+		reader.join();
+		rows.close(); writer.join();
+		f[0].close(); f[1].close();
+		st.t_read += t_read; st.t_write += t_write; st.t_gpu_wait += t_wait; st.t_total += now_s() - t_begin;
+		if(rc < 0) return -1;
+		return fallback ? 1 : 0;
+	}
+};
+
 static void write_report(const HostIndex& h, const Options& o, Species& sp) {   // centrifuge.cpp:3231-3319
 	std::cerr << "report file " << o.report << std::endl;
 	std::ofstream ro(o.report.c_str());
@@ -495,6 +727,8 @@ static int parse_args(int argc, const char** argv, Options& o, bool& exit_now) {
 		else if(key == "3" || key == "trim3") o.trim3 = atoi(val.c_str());
 		else if(key == "device") o.device = atoi(val.c_str());
 		else if(key == "batch-units") o.batch_units = (size_t)strtoull(val.c_str(), NULL, 10);
+		else if(key == "text-block-mb") { const size_t mb = (size_t)strtoull(val.c_str(), NULL, 10); o.text_block = std::min<size_t>(std::max<size_t>(mb, 1), 1024) << 20; }
+		else if(key == "host-parse") o.host_parse = true;
 		else if(key == "arg-desc") { print_arg_desc(); exit_now = true; return 0; }
 		else if(key == "version") { std::cout << "centrifuge-class (cfb200, B200-native) compatible with Centrifuge 1.0.4" << std::endl; exit_now = true; return 0; }
 		else if(key == "h" || key == "help") { std::cout << "Usage: centrifuge-class [options]* -x <cf-idx> {-1 <m1> -2 <m2> | -U <r>} [-S <out.tsv>] [--report-file <report>]" << std::endl; exit_now = true; return 0; }
@@ -506,6 +740,7 @@ static int parse_args(int argc, const char** argv, Options& o, bool& exit_now) {
 	if(o.mates1.size() != o.mates2.size()) { std::cerr << "Error: " << o.mates1.size() << " mate files/sequences were specified with -1, but " << o.mates2.size() << std::endl << "mate files/sequences were specified with -2.  The same number of mate files/" << std::endl << "sequences must be specified with -1 and -2." << std::endl; return 1; }
 	if(o.singles.empty() && o.mates1.empty()) { std::cerr << "No index, query, or output file specified!" << std::endl; return 1; }
 	if(o.batch_units < 1) o.batch_units = 1;
+	if(const char* e = getenv("CFB_TEXT_BLOCK")) o.text_block = std::max<size_t>((size_t)strtoull(e, NULL, 10), 4096);   // bytes; tests use tiny spans
 	return 0;
 }
 
@@ -517,11 +752,13 @@ extern "C" int cfb_run(int argc, const char** argv) {
 	try {
 		int rc = parse_args(argc, argv, o, exit_now);
 		if(rc || exit_now) return rc;
+		const auto t_start = std::chrono::steady_clock::now();
 		cfb_index* ix = NULL;
 		if(cfb_index_load(o.index.c_str(), o.device, &ix) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; return 1; }
 		cfb_ctx* ctx = NULL;
 		if(cfb_ctx_create(ix, &o.prm, &ctx) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; cfb_index_free(ix); return 1; }
 		const HostIndex& h = *cfb_index_host(ix);
+		const auto t_loaded = std::chrono::steady_clock::now();
 		FILE* fo = o.out == "-" ? stdout : fopen(o.out.c_str(), "wb");
 		if(!fo) { std::cerr << "Error: could not open output file " << o.out << std::endl; return 1; }
 		fputs("readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n", fo);
@@ -557,11 +794,29 @@ extern "C" int cfb_run(int argc, const char** argv) {
 		for(size_t i = 0; i < o.mates1.size(); i++) { Src s; s.a = o.mates1[i]; s.b = o.mates2[i]; s.paired = true; srcs.push_back(s); }
 		for(size_t i = 0; i < o.singles.size(); i++) { Src s; s.a = o.singles[i]; s.paired = false; srcs.push_back(s); }
 		bool stop = false;
+		MultiObs multi; TextStats tstats; uint64_t host_units = 0;
+		TextPipe pipe(ctx, o, fo, multi, tstats);
+		const bool text_ok = !o.host_parse && !getenv("CFB_HOST_PARSE") && o.prm.khits <= 32 && o.skip == 0 && o.upto == std::numeric_limits<uint64_t>::max();
 		for(size_t si = 0; si < srcs.size() && !failed && !stop; si++) {
+			uint64_t off[2] = {0, 0}, done = 0;
+			if(text_ok && srcs[si].a != "-" && srcs[si].b != "-") {
+				const int r = pipe.run(srcs[si].a, srcs[si].paired ? &srcs[si].b : NULL, off, done);
+				if(r < 0) { failed = true; break; }
+				rdid += done;
+				if(r == 0) continue;
+			}
 			FileIn fa, fb;
 			if(!fa.open(srcs[si].a)) { std::cerr << "Warning: Could not open read file \"" << srcs[si].a << "\" for reading; skipping..." << std::endl; continue; }
 			if(srcs[si].paired && !fb.open(srcs[si].b)) { std::cerr << "Warning: Could not open read file \"" << srcs[si].b << "\" for reading; skipping..." << std::endl; continue; }
-			bool firstA = true, firstB = true; uint64_t cntA = 0, cntB = 0;
+			bool firstA = true, firstB = true; uint64_t cntA = done, cntB = done;
+			// continue after the spans the text operator consumed: same parser state as if it had read them itself
+			auto resume = [&](FileIn& f, uint64_t at, bool& first) {
+				if(at == 0) return;
+				f.seek(at); first = false;
+				if(!o.fasta) { while(f.peek() == '\n' || f.peek() == '\r') f.get(); f.get(); }   // the '@' that ends the previous record's parse
+			};
+			resume(fa, off[0], firstA);
+			if(srcs[si].paired) resume(fb, off[1], firstB);
 			Rec ra, rb;
 			hb[cur].clear(srcs[si].paired);
 			for(;;) {
@@ -575,7 +830,7 @@ extern "C" int cfb_run(int argc, const char** argv) {
 				const uint64_t id = rdid++;
 				if(id >= o.upto) { stop = true; break; }
 				if(id < o.skip) continue;
-				hb[cur].add(ra, srcs[si].paired ? &rb : NULL, o.seed);
+				hb[cur].add(ra, srcs[si].paired ? &rb : NULL, o.seed); host_units++;
 				if(hb[cur].n >= o.batch_units) {
 					if(!flush(cur)) { failed = true; break; }
 					const int nxt = (cur + 1) % nslots;
@@ -589,6 +844,28 @@ extern "C" int cfb_run(int argc, const char** argv) {
 			if(!flush(cur)) { failed = true; break; }
 			for(int k = 1; k <= nslots; k++) { const int s = (cur + k) % nslots; if(busy[s] && !drain(s)) { failed = true; break; } }
 			hb[cur].clear(false);
+		}
+		if(!failed && tstats.units) {       // fold the device-side counters into the host maps
+			uint64_t n = 0;
+			if(cfb_text_species(ctx, NULL, NULL, NULL, NULL, 0, &n) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; failed = true; }
+			std::vector<uint64_t> tx(n), nr(n), nu(n), no(n);
+			if(!failed && n && cfb_text_species(ctx, tx.data(), nr.data(), nu.data(), no.data(), n, &n) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; failed = true; }
+			for(uint64_t i = 0; i < n && !failed; i++) {
+				Counts& c = sp.counts[tx[i]]; c.n_reads += nr[i]; c.n_unique += nu[i];
+				if(no[i]) sp.observed[std::vector<uint64_t>(1, tx[i])] += no[i];
+			}
+			for(MultiObs::const_iterator it = multi.begin(); it != multi.end(); ++it) {
+				std::vector<uint64_t> ids(it->first.size() / 8);
+				memcpy(ids.data(), it->first.data(), ids.size() * 8);
+				sp.observed[ids] += it->second;
+			}
+		}
+		if(getenv("CFB_TEXT_STATS")) {
+			const auto t_done = std::chrono::steady_clock::now();
+			std::cerr << "[cfb] index load " << std::chrono::duration<double>(t_loaded - t_start).count() << " s, reads " << std::chrono::duration<double>(t_done - t_loaded).count() << " s" << std::endl;
+			std::cerr << "[cfb] text operator: " << tstats.units << " units in " << tstats.spans << " spans (" << tstats.bytes_in << " bytes in, " << tstats.bytes_out
+			          << " bytes out, " << tstats.fallbacks << " fallbacks); record-level reader: " << host_units << " units" << std::endl;
+			std::cerr << "[cfb] text pipeline " << tstats.t_total << " s: reader busy " << tstats.t_read << " s, device wait " << tstats.t_gpu_wait << " s, writer busy " << tstats.t_write << " s" << std::endl;
 		}
 		if(fo != stdout) fclose(fo); else fflush(stdout);
 		if(!failed && !o.report.empty()) write_report(h, o, sp);

@@ -1366,7 +1366,7 @@ struct Slot {
 	HBuf<OutRec> h_recs; HBuf<uint32_t> h_rec_off;
 	// batch bookkeeping
 	BatchView bv; uint64_t n_units = 0, n_bases = 0; uint32_t maxlen = 0, cap = 0; uint64_t rows_cap = 0, dense_cap = 0;
-	bool pending = false;
+	bool pending = false, reran = false;
 	void release() {
 		h_bases.release(); h_off.release(); h_len.release(); h_flags.release(); d_bases.release(); d_off.release(); d_len.release(); d_flags.release();
 		pk.release(); nm.release(); hits.release(); nhits.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
@@ -1377,6 +1377,8 @@ struct Slot {
 };
 
 struct cfb_dbatch { int slot; };
+struct TextCtx;                       // cf_text.cuh
+static void text_release(cfb_ctx*);
 
 struct cfb_ctx {
 	const cfb_index* ix = nullptr;
@@ -1387,6 +1389,7 @@ struct cfb_ctx {
 	uint64_t launches = 0;
 	int search_blocks = 0, resolve_blocks = 0, group = 1; int resolve_mode = 2;   // 0 = 8-lane sides, 1 = thread/blocks, 2 = 4-lane rank16
 	cfb_dbatch resident; bool resident_used = false;
+	TextCtx* text = nullptr;
 };
 
 // every tree node whose ancestor chain contains a listed id (Classifier ctor classifier.h:157-201)
@@ -1408,6 +1411,7 @@ static void expand_taxids(const HostIndex& h, const uint64_t* ids, uint64_t n, s
 extern "C" void cfb_ctx_destroy(cfb_ctx* c) {
 	if(!c) return;
 	if(c->ix && c->ix->device >= 0) cudaSetDevice(c->ix->device);
+	text_release(c);
 	for(int i = 0; i < kSlots; i++) c->slots[i].release();
 	c->d_excl.release(); c->d_host.release();
 	if(c->d_ctr) cudaFree(c->d_ctr);
@@ -1612,12 +1616,12 @@ static int finish_batch(cfb_ctx* c, Slot& s, bool time_it, bool to_host, cfb_res
 		const unsigned ovf = (unsigned)(s.h_scal.p[2] & 0xffffffffu);
 		const uint64_t total_rows = s.h_scal.p[3];
 		if(ovf == 1) {            // hit-list capacity: only possible when the caller's flags bypass the N filter
-			s.cap = s.maxlen + 2;
+			s.cap = s.maxlen + 2; s.reran = true;
 			int rc = enqueue_kernels(c, s, 0, time_it); if(rc) return rc;
 			continue;
 		}
 		if(total_rows > s.rows_cap) {
-			s.rows_cap = total_rows + total_rows / 4 + 1024;
+			s.rows_cap = total_rows + total_rows / 4 + 1024; s.reran = true;
 			int rc = enqueue_kernels(c, s, 1, time_it); if(rc) return rc;
 			continue;
 		}
@@ -1733,3 +1737,5 @@ extern "C" int cfb_test_resolve(const cfb_index* ix, const uint64_t* rows, uint6
 	cudaFree(dr); cudaFree(dout); cudaFree(sc);
 	return CFB_OK;
 }
+
+#include "cf_text.cuh"

@@ -135,6 +135,43 @@ int  cfb_classify_resident(cfb_ctx*, cfb_dbatch*, float* kernel_ms, uint64_t* n_
 /* copy the last resident result to host (for parity checks) */
 int  cfb_resident_result(cfb_ctx*, cfb_result* out);
 
+/* ---- text-level operator: read-file bytes in, classification TSV out -------
+ * Replaces, for well-formed input, the per-read host work either side of Classifier::go:
+ *   FastqPatternSource/FastaPatternSource::parse + genRandSeed   pat.cpp:725-1157, pat.h:55-91
+ *   nFilter / lenfilt                                             centrifuge.cpp:2550-2596
+ *   AlnSinkWrap::finishRead -> selectByScore -> AlnSinkSam::append   aln_sink.h:1634-1927,2280-2337
+ *   SpeciesMetrics::addSpeciesCounts                              aln_sink.h:142-172
+ * `text_a` (`text_b` = mate 2 or NULL) hold exactly `n_records` complete records in the strict layout
+ * (FASTQ: 4 lines, FASTA: 2 lines per record, '\n' line ends, last line terminated) and start at a
+ * record start.  Tokenising, base conversion, filters, seeds, classification, tie selection and TSV
+ * formatting all run on the device; the host only moves bytes.  Anything the strict layout does not
+ * cover (CR, blank or wrapped lines, empty names or reads, short quality strings, more hits than the
+ * on-device selector holds) sets `irregular` and produces no output: the caller then parses that span
+ * with its own reader and uses cfb_classify_submit (cf_host.cpp does exactly that), so results never
+ * depend on which path ran. */
+typedef struct {
+	int32_t  fasta;            /* 0 = FASTQ, 1 = FASTA */
+	int32_t  trim5, trim3;
+	uint32_t seed;             /* --seed */
+	uint32_t maxlen_hint;      /* longest read expected (0 = unknown): sizes the first pass; longer reads only cost a re-run */
+} cfb_text_opts;
+typedef struct {
+	uint64_t n_units;
+	int32_t  irregular;        /* != 0: nothing was produced for this span */
+	uint32_t maxlen;
+	const char* tsv; uint64_t tsv_bytes;        /* rows in input order, pinned host memory */
+	/* reads whose best rows tie between several taxa at full score (SpeciesMetrics::observed keys of
+	 * size > 1): n_multi records of `multi_stride` u64 = {n, n taxids ascending, ...} */
+	const uint64_t* multi; uint64_t n_multi; uint32_t multi_stride;
+} cfb_text_result;
+int cfb_text_submit(cfb_ctx*, int slot, const void* text_a, uint64_t bytes_a, const void* text_b, uint64_t bytes_b,
+                    uint64_t n_records, const cfb_text_opts*);
+/* discard != 0: drop the span's contribution to the per-taxon counters (the caller re-does it). */
+int cfb_text_wait(cfb_ctx*, int slot, int discard, cfb_text_result* out);
+/* Per-taxon counters accumulated on the device by all accepted spans: entries with n_reads > 0.
+ * n_obs1 = reads whose single best row reached the maximum score (observed keys of size 1). */
+int cfb_text_species(cfb_ctx*, uint64_t* taxid, uint64_t* n_reads, uint64_t* n_unique, uint64_t* n_obs1, uint64_t cap, uint64_t* n);
+
 /* Operation counters of the last batch on this ctx (same definition as SURVEY.md 8d):
  * {units, partial_searches, ftab_probes, sides_search, walk_steps, rows_resolved, lf_steps_total, ext_searches} */
 int cfb_ctx_counters(cfb_ctx*, uint64_t out[8]);

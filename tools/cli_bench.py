@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""File-to-file throughput of the drop-in `centrifuge-class` (FASTQ in, TSV + report out) on a GPU box:
+the text operator (device tokeniser/formatter) against the record-level host reader and the reference
+binary on the same files.  Env: CFB_CLI_GENERA (default 100 -> 1 Gbp index), CFB_CLI_READS (10M)."""
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+EXE = os.path.join(ROOT, "centrifuge_b200", "centrifuge-class")
+REF = os.path.join(ROOT, "oracle", "_ref", "centrifuge-class")
+
+
+def fastq_matrix(codes, start=0):
+    """Fixed-width FASTQ records as one uint8 matrix (vectorised: 10M reads in seconds)."""
+    n, L = codes.shape
+    w = 2 + 9 + 1 + L + 3 + L + 1
+    m = np.empty((n, w), dtype=np.uint8)
+    m[:, 0] = ord("@"); m[:, 1] = ord("r")
+    idx = np.arange(start, start + n, dtype=np.int64)
+    m[:, 2:11] = (idx[:, None] // (10 ** np.arange(8, -1, -1, dtype=np.int64))[None, :] % 10 + 48).astype(np.uint8)
+    m[:, 11] = 10
+    m[:, 12:12 + L] = np.frombuffer(b"ACGTN", dtype=np.uint8)[codes]
+    m[:, 12 + L] = 10; m[:, 13 + L] = ord("+"); m[:, 14 + L] = 10
+    m[:, 15 + L:15 + 2 * L] = ord("I")
+    m[:, 15 + 2 * L] = 10
+    return m
+
+
+def run(exe, args, env=None):
+    t0 = time.time()
+    p = subprocess.run([exe] + args, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=dict(os.environ, **(env or {})))
+    dt = time.time() - t0
+    if p.returncode != 0:
+        raise RuntimeError(p.stderr.decode()[-2000:])
+    return dt, p.stderr.decode()
+
+
+def main():
+    genera = int(os.environ.get("CFB_CLI_GENERA", 100)); n = int(os.environ.get("CFB_CLI_READS", 10000000)); L = int(os.environ.get("CFB_CLI_RDLEN", 100))
+    base, d = bench.get_index(genera, 10, 1000000, 12345)
+    work = os.environ.get("CFB_CLI_DIR", "/dev/shm" if os.path.isdir("/dev/shm") else d)
+    fq = os.path.join(work, "cli_bench.fq"); small = os.path.join(work, "cli_bench_small.fq")
+    t0 = time.time()
+    with open(fq, "wb") as f:
+        for s in range(0, n, 2000000):
+            k = min(2000000, n - s)
+            codes = bench.make_reads(genera, 10, 1000000, 12345, k, L, 1000 + s)
+            m = fastq_matrix(codes, s)
+            if s == 0:
+                with open(small, "wb") as g:
+                    g.write(m[:200000].tobytes())
+            f.write(m.tobytes())
+    print("[cli_bench] %d reads, %.2f GB FASTQ written in %.1f s" % (n, os.path.getsize(fq) / 1e9, time.time() - t0), flush=True)
+    out = os.path.join(work, "cli_out.tsv"); rep = os.path.join(work, "cli_out.rep")
+
+    def stats(err):
+        return " | ".join(l for l in err.splitlines() if l.startswith("[cfb]"))
+
+    for tag, extra in (("text operator", []), ("text operator (2nd run)", []), ("host reader", ["--host-parse", "-u", str(min(n, 2000000))])):
+        dt, err = run(EXE, ["-q", "-x", base, "-U", fq, "-S", out, "--report-file", rep] + extra, {"CFB_TEXT_STATS": "1"})
+        print("[cli_bench] %s: wall %.2f s; %s" % (tag, dt, stats(err)), flush=True)
+    # same bytes as the reference on a subset
+    dt, err = run(EXE, ["-q", "-x", base, "-U", small, "-S", out + ".s", "--report-file", rep + ".s"], {"CFB_TEXT_STATS": "1"})
+    if os.path.exists(REF):
+        for p in (1, 16):
+            t, _ = run(REF, ["-q", "-p", str(p), "-x", base, "-U", small, "-S", out + ".r", "--report-file", rep + ".r"])
+            print("[cli_bench] reference -p %d on 200000 reads: wall %.2f s (incl. index load)" % (p, t), flush=True)
+            if p == 1:
+                same = open(out + ".s", "rb").read() == open(out + ".r", "rb").read() and open(rep + ".s", "rb").read() == open(rep + ".r", "rb").read()
+                print("[cli_bench] TSV + report identical to the reference on the subset: %s" % same, flush=True)
+    for f in (fq, small, out, rep, out + ".s", rep + ".s", out + ".r", rep + ".r"):
+        if os.path.exists(f):
+            os.remove(f)
+
+
+if __name__ == "__main__":
+    main()
