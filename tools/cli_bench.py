@@ -63,8 +63,13 @@ def main():
     def stats(err):
         return " | ".join(l for l in err.splitlines() if l.startswith("[cfb]"))
 
-    for tag, extra in (("text operator", []), ("text operator (2nd run)", []), ("host reader", ["--host-parse", "-u", str(min(n, 2000000))])):
-        dt, err = run(EXE, ["-q", "-x", base, "-U", fq, "-S", out, "--report-file", rep] + extra, {"CFB_TEXT_STATS": "1"})
+    runs = [("text operator", [], {}), ("text operator (2nd run)", [], {})]
+    for t in os.environ.get("CFB_CLI_THREAD_SWEEP", "").split(","):
+        if t:
+            runs.append(("text operator, %s read threads" % t, [], {"CFB_READ_THREADS": t}))
+    runs.append(("host reader", ["--host-parse", "-u", str(min(n, 2000000))], {}))
+    for tag, extra, env in runs:
+        dt, err = run(EXE, ["-q", "-x", base, "-U", fq, "-S", out, "--report-file", rep] + extra, dict(env, CFB_TEXT_STATS="1"))
         print("[cli_bench] %s: wall %.2f s; %s" % (tag, dt, stats(err)), flush=True)
     # same bytes as the reference on a subset
     dt, err = run(EXE, ["-q", "-x", base, "-U", small, "-S", out + ".s", "--report-file", rep + ".s"], {"CFB_TEXT_STATS": "1"})
