@@ -73,6 +73,21 @@ def make_reads(genera, species, length, gseed, n, rdlen, seed, device=0):
     return capi.synth_reads(synth_opts(genera, species, length, gseed, device=device), n, rdlen, seed)
 
 
+def fastq_matrix(codes, start=0):
+    """Fixed-width FASTQ records ("@r%09d", 4 lines) as one uint8 matrix, vectorised."""
+    n, L = codes.shape
+    m = np.empty((n, 2 + 9 + 1 + L + 3 + L + 1), dtype=np.uint8)
+    m[:, 0] = ord("@"); m[:, 1] = ord("r")
+    idx = np.arange(start, start + n, dtype=np.int64)
+    m[:, 2:11] = (idx[:, None] // (10 ** np.arange(8, -1, -1, dtype=np.int64))[None, :] % 10 + 48).astype(np.uint8)
+    m[:, 11] = 10
+    m[:, 12:12 + L] = np.frombuffer(b"ACGTN", dtype=np.uint8)[codes]
+    m[:, 12 + L] = 10; m[:, 13 + L] = ord("+"); m[:, 14 + L] = 10
+    m[:, 15 + L:15 + 2 * L] = ord("I")
+    m[:, 15 + 2 * L] = 10
+    return m
+
+
 def write_fastq(path, codes, prefix="r"):
     asc = np.frombuffer(b"ACGTN", dtype=np.uint8)[codes]
     n, L = asc.shape
@@ -334,6 +349,38 @@ def _main(result):
     if dist:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = world * n_e2e * a.steps / float(te[0])
+
+    # ---------------- e2e_text: FASTQ bytes in (pinned host memory), classification TSV bytes out, through the
+    # text-level operator (device tokeniser / selector / formatter): what the CLI does minus the file system.
+    txt = []
+    for sl in range(nslots):
+        fm = fastq_matrix(codes[sl * m:(sl + 1) * m], sl * m)
+        pt = capi.pinned_array((fm.size,), np.uint8); pt[:] = fm.reshape(-1)
+        txt.append(pt)
+
+    def text_step():
+        nb = 0
+        for sl in range(nslots):
+            ctx.text_submit(sl, txt[sl], None, m, maxlen_hint=a.rdlen)
+        for sl in range(nslots):
+            r = ctx.text_wait(sl, copy=False)
+            if r["irregular"]:
+                raise RuntimeError("text operator rejected the synthetic FASTQ")
+            nb += r["tsv_bytes"] + r["n_multi"] * 8 * 6
+        return nb
+
+    for _ in range(max(1, min(a.warmup, 2))):
+        text_step()
+    sync_all()
+    t0 = time.perf_counter()
+    tsv_bytes = 0
+    for s in range(a.steps):
+        tsv_bytes += text_step()
+    sync_all()
+    tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_text = world * n_e2e * a.steps / float(tt[0])
     sampler.stop_flag = True; sampler.join(timeout=2)
     launches_total = ctx.launches()
     h2d = bases.nbytes + offs.nbytes + lens.nbytes + flags.nbytes
@@ -357,6 +404,8 @@ def _main(result):
         "config": {"workload": workload, "index_bytes_hbm": int(ix.info.device_bytes), "l2": "index replica %.0f MB vs 126 MB L2; same batch re-walked every step" % (ix.info.device_bytes / 1e6),
                    "parallelism": "reads sharded over %d GPU(s), index replicated, 1 NCCL all-reduce of per-taxon counts per step" % world},
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h // max(a.steps, 1))},
+        "e2e_text": {"value": e2e_text, "unit": "reads/s", "what": "FASTQ text in pinned host memory -> TSV rows in host memory (cfb_text_submit/wait)",
+                     "h2d_bytes_per_step": int(sum(t.nbytes for t in txt)), "d2h_bytes_per_step": int(tsv_bytes // max(a.steps, 1))},
         "gpu_launches": int(launches_value),
         "roofline": {"bound": "hbm", "kernel": "k_search_t", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "random_gather": gather,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_search), "kernel_ms": 1000 * search_s,

@@ -150,6 +150,15 @@ def _result(res):
     return off, recs
 
 
+class TextOpts(C.Structure):
+    _fields_ = [("fasta", C.c_int32), ("trim5", C.c_int32), ("trim3", C.c_int32), ("seed", C.c_uint32), ("maxlen_hint", C.c_uint32)]
+
+
+class TextResultC(C.Structure):
+    _fields_ = [("n_units", C.c_uint64), ("irregular", C.c_int32), ("maxlen", C.c_uint32), ("tsv", C.c_void_p), ("tsv_bytes", C.c_uint64),
+                ("multi", C.POINTER(C.c_uint64)), ("n_multi", C.c_uint64), ("multi_stride", C.c_uint32)]
+
+
 class Context:
     def __init__(self, index, params=None):
         self.index = index
@@ -186,6 +195,32 @@ class Context:
         res = ResultC()
         _ck(lib().cfb_resident_result(self.h, C.byref(res)))
         return _result(res)
+
+    def text_submit(self, slot, text_a, text_b=None, n_records=0, fasta=False, trim5=0, trim3=0, seed=0, maxlen_hint=0):
+        """text_a/text_b: uint8 arrays of complete records (pinned arrays are DMA'd in place)."""
+        o = TextOpts(1 if fasta else 0, trim5, trim3, seed, maxlen_hint)
+        pb = _p(text_b, C.c_uint8) if text_b is not None else None
+        _ck(lib().cfb_text_submit(self.h, C.c_int(slot), _p(text_a, C.c_uint8), C.c_uint64(text_a.size), pb,
+                                  C.c_uint64(text_b.size if text_b is not None else 0), C.c_uint64(n_records), C.byref(o)))
+
+    def text_wait(self, slot, discard=False, copy=True):
+        r = TextResultC()
+        _ck(lib().cfb_text_wait(self.h, C.c_int(slot), C.c_int(1 if discard else 0), C.byref(r)))
+        out = dict(n_units=int(r.n_units), irregular=int(r.irregular), maxlen=int(r.maxlen), tsv_bytes=int(r.tsv_bytes), n_multi=int(r.n_multi))
+        if copy and not r.irregular:
+            out["tsv"] = C.string_at(r.tsv, r.tsv_bytes) if r.tsv_bytes else b""
+            st = int(r.multi_stride)
+            out["multi"] = np.ctypeslib.as_array(r.multi, shape=(int(r.n_multi), st)).copy() if r.n_multi else np.zeros((0, st), dtype=np.uint64)
+        return out
+
+    def text_species(self):
+        n = C.c_uint64()
+        _ck(lib().cfb_text_species(self.h, None, None, None, None, C.c_uint64(0), C.byref(n)))
+        k = int(n.value)
+        arrs = [np.zeros(k, dtype=np.uint64) for _ in range(4)]
+        if k:
+            _ck(lib().cfb_text_species(self.h, *[_p(a, C.c_uint64) for a in arrs], C.c_uint64(k), C.byref(n)))
+        return dict(taxid=arrs[0], n_reads=arrs[1], n_unique=arrs[2], n_obs1=arrs[3])
 
     def counters(self):
         out = (C.c_uint64 * 8)()

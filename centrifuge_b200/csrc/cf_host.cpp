@@ -55,6 +55,7 @@ struct Options {
 	size_t batch_units = 1u << 18;
 	size_t text_block = 64u << 20;      // bytes of read file per device span (text operator)
 	bool host_parse = false;            // force the host reader / formatter
+	std::string kreport; bool kr_zeros = false, kr_has_score = false, kr_has_len = false; long long kr_min_score = 0, kr_min_len = 0;
 	cfb_params prm; std::vector<uint64_t> host, excl;
 	int trim5 = 0, trim3 = 0;
 };
@@ -64,7 +65,8 @@ static const OptDesc kLong[] = {
 	{"quiet", 0}, {"time", 0}, {"seed", 1}, {"upto", 1}, {"qupto", 1}, {"skip", 1}, {"version", 0}, {"help", 0}, {"threads", 1},
 	{"reorder", 0}, {"mm", 0}, {"wrapper", 1}, {"arg-desc", 0}, {"report-file", 1}, {"no-abundance", 0}, {"no-traverse", 0},
 	{"min-hitlen", 1}, {"host-taxids", 1}, {"exclude-taxids", 1}, {"classification-rank", 1}, {"trim5", 1}, {"trim3", 1},
-	{"device", 1}, {"batch-units", 1}, {"text-block-mb", 1}, {"host-parse", 0}, {NULL, 0}};
+	{"device", 1}, {"batch-units", 1}, {"text-block-mb", 1}, {"host-parse", 0},
+	{"kreport-file", 1}, {"kreport-show-zeros", 0}, {"kreport-min-score", 1}, {"kreport-min-length", 1}, {NULL, 0}};
 static const char* kShort = "fqtu:s:p:k:1:2:U:x:S:3:5:h";
 
 std::vector<std::string> split(const std::string& s, char d) {
@@ -439,6 +441,125 @@ struct Formatter {
 };
 
 
+// ------------------------------------------------------------------------------ Kraken-style report
+// In-process equivalent of the reference's `centrifuge-kreport` script, fed with the
+// classification rows while they are still in memory instead of re-reading the TSV.  Same algorithm on the
+// same text: rows of one read (equal consecutive readID strings) are merged to their LCA
+// (centrifuge-kreport:84-123), clade sums by DFS from node 1 (:219-228), children sorted by clade count,
+// stable (:150-156); taxonomy as `centrifuge-inspect --taxonomy-tree/--name-table` prints it
+// (centrifuge_inspect.cpp:534-550: ascending taxid).
+struct KReport {
+	const HostIndex& h; const Options& o;
+	std::unordered_map<uint64_t, long long> taxo; long long seq_count = 0;
+	std::string prev_id; uint64_t prev_tax = 0; bool have_prev = false;
+	std::unordered_map<uint64_t, bool> in_tree_cache;
+	uint64_t last_key = ~0ull; long long* last_ctr = NULL;
+	KReport(const HostIndex& h_, const Options& o_) : h(h_), o(o_) { taxo[0] = 0; }
+	bool enabled() const { return !o.kreport.empty(); }
+	bool parent_of(uint64_t t, uint64_t& p) const {          // %parent_map: node 1 hangs under 0
+		const TaxNode* n = h.find_node(t);
+		if(!n) return false;
+		p = t == 1 ? 0 : n->parent;
+		return true;
+	}
+	bool in_tree(uint64_t t) {                                // isTaxIDInTree :160-174
+		std::unordered_map<uint64_t, bool>::const_iterator it = in_tree_cache.find(t);
+		if(it != in_tree_cache.end()) return it->second;
+		bool ok = true;
+		for(uint64_t a = t; a > 1;) { uint64_t p; if(!parent_of(a, p)) { std::cerr << "Couldn't find parent of taxID " << a << " - directly assigned to root." << std::endl; ok = false; break; } if(p == a) break; a = p; }
+		in_tree_cache[t] = ok;
+		return ok;
+	}
+	uint64_t lca(uint64_t a, uint64_t b) {                    // :176-203
+		if(a == 0) return b;
+		if(b == 0) return a;
+		if(a == b) return a;
+		std::set<uint64_t> path;
+		while(a >= 1) { path.insert(a); uint64_t p; if(!parent_of(a, p)) break; if(p == a) break; a = p; }
+		while(b > 1) { if(path.count(b)) return b; uint64_t p; if(!parent_of(b, p)) break; if(p == b) break; b = p; }
+		return 1;
+	}
+	inline long long& ctr(uint64_t t) { if(t != last_key || !last_ctr) { last_ctr = &taxo[t]; last_key = t; } return *last_ctr; }
+	static inline long long num(const char* p, const char* e) { long long v = 0; bool neg = false; if(p < e && *p == '-') { neg = true; p++; } for(; p < e && *p >= '0' && *p <= '9'; p++) v = v * 10 + (*p - '0'); return neg ? -v : v; }
+	void consume(const char* p, size_t n) {                   // complete classification rows, header excluded
+		const char* end = p + n;
+		while(p < end) {
+			const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+			const char* le = nl ? nl : end;
+			const char* c[8]; int k = 0; c[0] = p;
+			for(const char* q = p; q < le && k < 7; ) { const char* t = (const char*)memchr(q, '\t', (size_t)(le - q)); if(!t) break; c[++k] = t + 1; q = t + 1; }
+			p = nl ? nl + 1 : end;
+			if(k < 7) continue;
+			const char* id = c[0]; const size_t idl = (size_t)(c[1] - 1 - c[0]);
+			if(o.kr_has_len && num(c[5], c[6] - 1) < o.kr_min_len) continue;
+			if(o.kr_has_score && num(c[3], c[4] - 1) < o.kr_min_score) continue;
+			uint64_t tax = 0; bool dotted = false;
+			for(const char* q = c[2]; q < c[3] - 1; q++) { if(*q == '.') { dotted = true; break; } tax = tax * 10 + (uint64_t)(*q - '0'); }
+			if(dotted) { std::cerr << "Couldn't find parent of taxID " << std::string(c[2], c[3] - 1) << " - directly assigned to root." << std::endl; tax = 1; }
+			else if(!in_tree(tax)) tax = 1;
+			if(have_prev && idl == prev_id.size() && memcmp(id, prev_id.data(), idl) == 0) {
+				ctr(prev_tax) -= 1; prev_tax = lca(prev_tax, tax); ctr(prev_tax) += 1;
+			} else { ctr(tax) += 1; seq_count++; prev_tax = tax; prev_id.assign(id, idl); }
+			have_prev = true;
+		}
+	}
+	static const char* rank_code(const char* r) {
+		static const char* const tab[][2] = {{"species", "S"}, {"genus", "G"}, {"family", "F"}, {"order", "O"}, {"class", "C"}, {"phylum", "P"}, {"kingdom", "K"}, {"superkingdom", "D"}};
+		for(size_t i = 0; i < 8; i++) if(strcmp(r, tab[i][0]) == 0) return tab[i][1];
+		return "-";
+	}
+	void write() {
+		if(seq_count <= 0) { std::cerr << "No sequence matches with given settings" << std::endl; return; }
+		FILE* f = fopen(o.kreport.c_str(), "wb");
+		if(!f) { std::cerr << "Error: could not open kreport file " << o.kreport << std::endl; return; }
+		std::map<uint64_t, std::vector<uint64_t> > child;
+		for(size_t i = 0; i < h.nodes.size(); i++) { const uint64_t t = h.nodes[i].taxid; child[t == 1 ? 0 : h.nodes[i].parent].push_back(t); }
+		std::unordered_map<uint64_t, long long> clade(taxo.begin(), taxo.end());
+		{   // dfs_summation(1), post-order
+			std::vector<std::pair<uint64_t, size_t> > st; std::set<uint64_t> seen;
+			st.push_back(std::make_pair((uint64_t)1, (size_t)0)); seen.insert(1);
+			while(!st.empty()) {
+				const uint64_t node = st.back().first; std::map<uint64_t, std::vector<uint64_t> >::const_iterator ch = child.find(node);
+				if(ch != child.end() && st.back().second < ch->second.size()) {
+					const uint64_t c = ch->second[st.back().second++];
+					if(seen.insert(c).second) st.push_back(std::make_pair(c, (size_t)0));
+				} else {
+					st.pop_back();
+					if(!st.empty()) { std::unordered_map<uint64_t, long long>::const_iterator v = clade.find(node); clade[st.back().first] += (v == clade.end() ? 0 : v->second); }
+				}
+			}
+		}
+		const double total = (double)seq_count;
+		fprintf(f, "%6.2f\t%lld\t%lld\t%s\t%d\t%s%s\n", (double)clade[0] * 100 / total, clade[0], taxo[0], "U", 0, "", "unclassified");
+		struct Frame { uint64_t node; int depth; };
+		std::vector<Frame> st; st.push_back(Frame{1, 0});
+		std::set<uint64_t> seen;
+		while(!st.empty()) {
+			const Frame fr = st.back(); st.pop_back();
+			std::unordered_map<uint64_t, long long>::const_iterator cv = clade.find(fr.node);
+			const long long cl = cv == clade.end() ? 0 : cv->second;
+			if(!cl && !o.kr_zeros) continue;
+			if(!seen.insert(fr.node).second) continue;
+			std::unordered_map<uint64_t, long long>::const_iterator tv = taxo.find(fr.node);
+			const TaxNode* nd = h.find_node(fr.node);
+			std::map<uint64_t, std::string>::const_iterator nm = (fr.node >> 32) ? h.names.end() : h.names.find(fr.node);
+			fprintf(f, "%6.2f\t%lld\t%lld\t%s\t%llu\t", (double)cl * 100 / total, cl, tv == taxo.end() ? 0ll : tv->second, rank_code(nd ? rank_name(nd->rank) : ""), (unsigned long long)fr.node);
+			for(int i = 0; i < fr.depth; i++) fputs("  ", f);
+			fputs(nm != h.names.end() ? nm->second.c_str() : "", f); fputc('\n', f);
+			std::map<uint64_t, std::vector<uint64_t> >::const_iterator ch = child.find(fr.node);
+			if(ch != child.end()) {
+				std::vector<uint64_t> kids = ch->second;
+				std::stable_sort(kids.begin(), kids.end(), [&](uint64_t a, uint64_t b) {
+					std::unordered_map<uint64_t, long long>::const_iterator x = clade.find(a), y = clade.find(b);
+					return (x == clade.end() ? 0 : x->second) > (y == clade.end() ? 0 : y->second); });
+				for(size_t i = kids.size(); i-- > 0;) st.push_back(Frame{kids[i], fr.depth + 1});    // reversed: the stack pops them in sorted order
+			}
+		}
+		fclose(f);
+	}
+};
+
+
 // ------------------------------------------------------------------------------ text operator driver
 // Well-formed FASTQ/FASTA goes to the device as raw bytes (cfb_text_submit): this thread only reads the
 // file into pinned memory, counts line ends to cut spans at record boundaries, and writes the rows that
@@ -526,7 +647,7 @@ template <class T> struct Chan {        // small blocking queue between the pipe
 // Three threads per source: a reader that fills pinned buffers and cuts spans at record boundaries, this
 // thread submitting spans to the device and collecting them in order, and a writer for the rows.
 struct TextPipe {
-	cfb_ctx* ctx; const Options& o; FILE* fo; MultiObs& multi; TextStats& st;
+	cfb_ctx* ctx; const Options& o; FILE* fo; MultiObs& multi; TextStats& st; KReport* kr = NULL;
 	int nslots = 0; size_t cap = 0; int read_threads = 8;
 	std::vector<unsigned char*> buf[2];
 	TextPipe(cfb_ctx* c, const Options& o_, FILE* f, MultiObs& m, TextStats& s) : ctx(c), o(o_), fo(f), multi(m), st(s) {
@@ -597,6 +718,7 @@ struct TextPipe {
 			while(rows.pop(r)) {
 				const double t0 = now_s();
 				if(r.tsv_bytes) fwrite(r.tsv, 1, r.tsv_bytes, fo);
+				if(kr && r.tsv_bytes) kr->consume(r.tsv, r.tsv_bytes);
 				for(uint64_t i = 0; i < r.n_multi; i++) {
 					const uint64_t* rec = r.multi + i * r.stride;
 					multi[std::string((const char*)(rec + 1), (size_t)rec[0] * 8)] += 1;
@@ -739,6 +861,10 @@ static int parse_args(int argc, const char** argv, Options& o, bool& exit_now) {
 		else if(key == "batch-units") o.batch_units = (size_t)strtoull(val.c_str(), NULL, 10);
 		else if(key == "text-block-mb") { const size_t mb = (size_t)strtoull(val.c_str(), NULL, 10); o.text_block = std::min<size_t>(std::max<size_t>(mb, 1), 1024) << 20; }
 		else if(key == "host-parse") o.host_parse = true;
+		else if(key == "kreport-file") o.kreport = val;
+		else if(key == "kreport-show-zeros") o.kr_zeros = true;
+		else if(key == "kreport-min-score") { o.kr_has_score = true; o.kr_min_score = atoll(val.c_str()); }
+		else if(key == "kreport-min-length") { o.kr_has_len = true; o.kr_min_len = atoll(val.c_str()); }
 		else if(key == "arg-desc") { print_arg_desc(); exit_now = true; return 0; }
 		else if(key == "version") { std::cout << "centrifuge-class (cfb200, B200-native) compatible with Centrifuge 1.0.4" << std::endl; exit_now = true; return 0; }
 		else if(key == "h" || key == "help") { std::cout << "Usage: centrifuge-class [options]* -x <cf-idx> {-1 <m1> -2 <m2> | -U <r>} [-S <out.tsv>] [--report-file <report>]" << std::endl; exit_now = true; return 0; }
@@ -756,6 +882,42 @@ static int parse_args(int argc, const char** argv, Options& o, bool& exit_now) {
 
 }  // namespace
 
+// Stand-alone form of the same report: classification TSV file in, Kraken-style report out (host only).
+extern "C" int cfb_kreport(const char* index_base, const char* tsv_path, const char* out_path, int show_zeros,
+                           int has_min_score, long long min_score, int has_min_length, long long min_length) {
+	if(!index_base || !tsv_path || !out_path) return CFB_EINVAL;
+	cfb_index* ix = NULL;
+	if(cfb_index_load(index_base, -1, &ix) != CFB_OK) return CFB_EIO;
+	Options o; o.kreport = out_path; o.kr_zeros = show_zeros != 0; o.kr_has_score = has_min_score != 0; o.kr_min_score = min_score;
+	o.kr_has_len = has_min_length != 0; o.kr_min_len = min_length;
+	int rc = CFB_OK;
+	{
+		KReport kr(*cfb_index_host(ix), o);
+		FILE* f = strcmp(tsv_path, "-") == 0 ? stdin : fopen(tsv_path, "rb");
+		if(!f) rc = CFB_EIO;
+		else {
+			std::vector<char> buf(1 << 22); size_t have = 0; bool header = true;
+			for(;;) {
+				const size_t r = fread(buf.data() + have, 1, buf.size() - have, f);
+				have += r;
+				if(have == 0) break;
+				size_t upto = have;
+				if(r != 0) { const void* q = memrchr(buf.data(), '\n', have); upto = q ? (size_t)((const char*)q - buf.data()) + 1 : 0; }
+				if(upto == 0 && r != 0) { buf.resize(buf.size() * 2); continue; }
+				size_t from = 0;
+				if(header) { const void* q = memchr(buf.data(), '\n', upto); from = q ? (size_t)((const char*)q - buf.data()) + 1 : upto; header = false; }
+				kr.consume(buf.data() + from, upto - from);
+				memmove(buf.data(), buf.data() + upto, have - upto); have -= upto;
+				if(r == 0) break;
+			}
+			if(f != stdin) fclose(f);
+			kr.write();
+		}
+	}
+	cfb_index_free(ix);
+	return rc;
+}
+
 extern "C" int cfb_run(int argc, const char** argv) {
 	init_tables();
 	Options o; bool exit_now = false;
@@ -772,7 +934,7 @@ extern "C" int cfb_run(int argc, const char** argv) {
 		FILE* fo = o.out == "-" ? stdout : fopen(o.out.c_str(), "wb");
 		if(!fo) { std::cerr << "Error: could not open output file " << o.out << std::endl; return 1; }
 		fputs("readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n", fo);
-		Species sp; Formatter fmt(h, o, sp);
+		Species sp; Formatter fmt(h, o, sp); KReport kr(h, o);
 		const int nslots = cfb_ctx_slots(ctx);
 		std::vector<HostBatch> hb(nslots);
 		std::vector<bool> busy(nslots, false);
@@ -783,6 +945,7 @@ extern "C" int cfb_run(int argc, const char** argv) {
 			if(cfb_classify_wait(ctx, s, &res) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; return false; }
 			fmt.format_batch(hb[s], res);
 			if(!fmt.out.empty()) fwrite(fmt.out.data(), 1, fmt.out.size(), fo);
+			if(kr.enabled() && !fmt.out.empty()) kr.consume(fmt.out.data(), fmt.out.size());
 			busy[s] = false;
 			return true;
 		};
@@ -806,6 +969,7 @@ extern "C" int cfb_run(int argc, const char** argv) {
 		bool stop = false;
 		MultiObs multi; TextStats tstats; uint64_t host_units = 0;
 		TextPipe pipe(ctx, o, fo, multi, tstats);
+		if(kr.enabled()) pipe.kr = &kr;
 		const bool text_ok = !o.host_parse && !getenv("CFB_HOST_PARSE") && o.prm.khits <= 32 && o.skip == 0 && o.upto == std::numeric_limits<uint64_t>::max();
 		for(size_t si = 0; si < srcs.size() && !failed && !stop; si++) {
 			uint64_t off[2] = {0, 0}, done = 0;
@@ -879,6 +1043,7 @@ extern "C" int cfb_run(int argc, const char** argv) {
 		}
 		if(fo != stdout) fclose(fo); else fflush(stdout);
 		if(!failed && !o.report.empty()) write_report(h, o, sp);
+		if(!failed && kr.enabled()) kr.write();
 		cfb_ctx_destroy(ctx); cfb_index_free(ix);
 		return failed ? 1 : 0;
 	} catch(int e) {

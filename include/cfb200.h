@@ -219,6 +219,13 @@ int cfb_synth_fasta(const cfb_build_opts* o, const char* path);
  * are rejected with exit code 1 like the reference's getopt table does. */
 int cfb_run(int argc, const char** argv);
 
+/* Kraken-style report.  Replaces the `centrifuge-kreport` script (centrifuge-kreport:60-260,
+ * default LCA mode; its --show-zeros / --min-score / --min-length options): same bytes from the same classification
+ * TSV and index.  cfb_run produces the same report in-process with `--kreport-file F` (plus --kreport-show-zeros,
+ * --kreport-min-score N, --kreport-min-length N) from the rows while they are still in memory.  Host only. */
+int cfb_kreport(const char* index_base, const char* tsv_path, const char* out_path, int show_zeros,
+                int has_min_score, long long min_score, int has_min_length, long long min_length);
+
 #ifdef __cplusplus
 }
 #endif
