@@ -52,6 +52,7 @@ struct IndexView {
 	const uint16_t* rtab16;         // device-only resolve table: sequence id of EVERY SA row (one of rtab16/rtab32, or neither)
 	const uint32_t* rtab32;
 	const uint64_t* ftabk;          // device-only extended jump table: (top, bot) per K-mer, K = ftabk_chars (0 = absent)
+	const uint64_t* walk8;          // device-only: per SA row, the row 8 LF steps on | the 8 BWT bases met << 40 | #valid steps << 56 (null = absent)
 	uint64_t len, zoff, zside, fchr[4], last_boundary, num_sides, num_blocks;
 	uint32_t zoffc, n_boundaries, n_seqs, n_host;
 	int32_t  off_rate, ftab_chars, bshift, ftabk_chars;

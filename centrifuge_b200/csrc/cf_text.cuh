@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) k_tok_rec(const TextArgs a) {
 	}
 	if(bad) { atomicOr(a.tscal, (unsigned long long)TX_IRREGULAR); return; }
 	const uint32_t len = trimmed_len(nread, a.trim5, a.trim3);
-	atomicMax(a.tscal + 1, (unsigned long long)len);
+	if((unsigned long long)len > *(volatile unsigned long long*)(a.tscal + 1)) atomicMax(a.tscal + 1, (unsigned long long)len);   // guarded: one address for all records
 	if(len > a.maxlen_hint) return;            // buffers are sized for the hint: the host re-runs the span with a wider class
 	a.len[m][r] = len;
 	a.seq_off[m][r] = s1; a.qual_off[m][r] = qoff;
@@ -158,25 +158,42 @@ __global__ void __launch_bounds__(128) k_tok_bases(const TextArgs a) {
 		if(m == 1 && lane == 0) a.off[1][u] = boff;         // BatchView offsets are absolute
 		uint8_t* dst = a.bases + boff;
 		uint32_t sx = 0, ns = 0;
-		for(uint32_t i = lane; i < line; i += 32) {
-			uint32_t c = t[so + i];
-			if(a.fasta) { if(!is_dnacat(c)) bad = true; }
-			else { if(c == '.') c = 'N'; if(!is_alpha(c)) bad = true; }
-			const uint32_t code = dna_code(c);
-			if(i >= (uint32_t)a.trim5 && i - a.trim5 < len) {
-				const uint32_t j = i - a.trim5;
-				dst[j] = (uint8_t)code;
-				sx ^= code << ((j & 15) << 1);
-				ns += code == 4;
+		for(uint32_t i4 = lane * 4; i4 < line; i4 += 128) {          // 4 characters per lane
+			const uint32_t v = load4(t, (uint64_t)so + i4);
+			uint32_t codes = 0, nvalid = 0;
+			#pragma unroll
+			for(uint32_t b = 0; b < 4; b++) {
+				const uint32_t i = i4 + b;
+				if(i >= line) break;
+				uint32_t c = (v >> (8 * b)) & 0xffu;
+				if(a.fasta) { if(!is_dnacat(c)) bad = true; }
+				else { if(c == '.') c = 'N'; if(!is_alpha(c)) bad = true; }
+				const uint32_t code = dna_code(c);
+				if(i >= (uint32_t)a.trim5 && i - a.trim5 < len) {
+					const uint32_t j = i - a.trim5;
+					codes |= code << (8 * b); nvalid++;
+					sx ^= code << ((j & 15) << 1);
+					ns += code == 4;
+				}
 			}
+			if(nvalid == 4 && ((boff + (i4 - a.trim5)) & 3ull) == 0) *reinterpret_cast<uint32_t*>(dst + (i4 - a.trim5)) = codes;
+			else for(uint32_t b = 0; b < 4; b++) { const uint32_t i = i4 + b; if(i < line && i >= (uint32_t)a.trim5 && i - a.trim5 < len) dst[i - a.trim5] = (uint8_t)(codes >> (8 * b)); }
 		}
-		for(uint32_t j = lane; j < len; j += 32) {          // quality contribution ('I' for FASTA, pat.cpp:828)
-			const uint32_t q = a.fasta ? (uint32_t)'I' : (uint32_t)t[qo + a.trim5 + j];
-			sx ^= q << ((j & 3) << 3);
-		}
-		if(!a.fasta) {                                       // phred33 characters only (qual.h:136-142; a space is an error too)
+		if(a.fasta) {                                        // every FASTA base has quality 'I' (pat.cpp:828)
+			for(uint32_t j = lane; j < len; j += 32) sx ^= (uint32_t)'I' << ((j & 3) << 3);
+		} else {
+			for(uint32_t j4 = lane * 4; j4 < len; j4 += 128) {    // quality contribution: byte (j & 3) of the seed word
+				const uint32_t v = load4(t, (uint64_t)qo + a.trim5 + j4);
+				const uint32_t keep = len - j4 >= 4 ? 0xffffffffu : ((1u << (8 * (len - j4))) - 1u);
+				sx ^= v & keep;
+			}
+			// phred33 characters only (qual.h:136-142; a space is an error too)
 			const uint32_t qlen = a.nl[m][u * a.lines_per + 3] - qo;
-			for(uint32_t j = lane; j < qlen; j += 32) { const uint32_t q = t[qo + j]; if(q < 33 || q > 127) bad = true; }
+			for(uint32_t j4 = lane * 4; j4 < qlen; j4 += 128) {
+				const uint32_t v = load4(t, (uint64_t)qo + j4);
+				const uint32_t keep = qlen - j4 >= 4 ? 0xffffffffu : ((1u << (8 * (qlen - j4))) - 1u);
+				if((__vcmpltu4(v, 0x21212121u) | __vcmpgtu4(v, 0x7f7f7f7fu)) & keep) bad = true;
+			}
 		}
 		// name: up to the first '/' (pat.h:84-88); chars are signed in the reference
 		bool slashed = false;

@@ -57,6 +57,17 @@ __device__ __forceinline__ uint64_t shr64(uint64_t v, uint32_t n) {
 // =======================================================================================
 struct PackArgs { BatchView b; uint64_t* pk; uint32_t* nm; uint32_t W; };
 
+// 4 bytes at an arbitrary byte offset of a 4-byte aligned buffer (reads at most 7 bytes past `off`: device
+// buffers carry that much slack)
+__device__ __forceinline__ uint32_t load4(const uint8_t* base, uint64_t off) {
+	const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (off & ~3ull));
+	return __funnelshift_r(w[0], w[1], (uint32_t)(off & 3) * 8);
+}
+
+// four 2-bit fields held one per byte -> 8 contiguous bits; four 1-bit flags held one per byte -> 4 bits
+__device__ __forceinline__ uint32_t squeeze4x2(uint32_t x) { x = (x | (x >> 6)) & 0x000F000Fu; return (x | (x >> 12)) & 0xFFu; }
+__device__ __forceinline__ uint32_t squeeze4x1(uint32_t x) { x = (x | (x >> 7)) & 0x00030003u; return (x | (x >> 14)) & 0xFu; }
+
 __global__ void __launch_bounds__(128) k_pack(const PackArgs a) {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (task, word)
 	const uint64_t ntasks = (uint64_t)a.b.n_units * a.b.n_mates * 2;
@@ -65,15 +76,32 @@ __global__ void __launch_bounds__(128) k_pack(const PackArgs a) {
 	const uint32_t per = 2u * (uint32_t)a.b.n_mates;
 	const uint32_t unit = (uint32_t)(t / per), rem = (uint32_t)(t - (uint64_t)unit * per);
 	const int mate = (int)(rem >> 1), strand = (int)(rem & 1);
-	const uint32_t len = a.b.len[mate][unit];
-	const uint8_t* fw = a.b.bases + a.b.off[mate][unit];
+	const uint32_t len = mate ? a.b.len[1][unit] : a.b.len[0][unit];        // no runtime index into the parameter arrays
 	uint64_t w = 0; uint32_t n = 0;
-	for(uint32_t q = 0; q < 32; q++) {
-		const uint32_t p = k * 32 + q;
-		if(p >= len) break;
-		int c = strand == 0 ? fw[len - 1 - p] : fw[p];
-		if(c > 3) { n |= 1u << q; c = 0; } else if(strand) c = 3 - c;
-		w |= (uint64_t)c << (2 * q);
+	if(k * 32 < len) {
+		const uint64_t off = mate ? a.b.off[1][unit] : a.b.off[0][unit];
+		const uint32_t cnt = min(32u, len - k * 32);         // bases of this word
+		// strand 1 consumes fw[p], strand 0 consumes fw[len-1-p]: either way a window of `cnt` consecutive bytes,
+		// packed in window order four bytes at a time and flipped end to end for strand 0
+		const uint64_t lo = strand ? off + k * 32 : off + (len - k * 32 - cnt);
+		#pragma unroll
+		for(uint32_t g = 0; g < 32; g += 4) {
+			if(g < cnt) {
+				const uint32_t keep = cnt - g >= 4 ? 0xffffffffu : ((1u << (8 * (cnt - g))) - 1u);
+				const uint32_t v = load4(a.b.bases, lo + g) & keep;
+				const uint32_t nb = __vcmpne4(v & 0xFCFCFCFCu, 0u) & 0x01010101u;        // codes above 3 are N
+				uint32_t b2 = v & 0x03030303u;
+				if(strand) b2 ^= 0x03030303u & keep;
+				b2 &= ~(nb * 3u);
+				w |= (uint64_t)squeeze4x2(b2) << (2 * g);
+				n |= squeeze4x1(nb) << g;
+			}
+		}
+		if(!strand) {
+			uint64_t x = __brevll(w);
+			x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+			w = x >> (2 * (32 - cnt)); n = __brev(n) >> (32 - cnt);
+		}
 	}
 	a.pk[i] = w; a.nm[i] = n;
 }
@@ -525,6 +553,7 @@ __global__ void k_build_ftab2(IndexView v, uint64_t n, uint64_t* ftab2) {
 	ftab2[fi * 2] = ftab_hi(v, v.ftab[fi]); ftab2[fi * 2 + 1] = ftab_lo(v, v.ftab[fi + 1]);
 }
 static const uint64_t kOccMask = 0x7fffffffffffffffull;
+static const uint64_t kWalkRowMask = (1ull << 40) - 1ull;   // walk8 entry: row in the low 40 bits
 
 // Extended jump table: the SA range of every K-mer (K > ftabChars), obtained by K - ftabChars LF steps from the
 // 10-mer range -- exactly what partialSearch would compute base by base (hi_aligner.h:985-1008).  It trades
@@ -614,9 +643,10 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 	const ulonglong2* ftabk = reinterpret_cast<const ulonglong2*>(a.v.ftabk);
 	const uint32_t fk = (COUNT || !a.v.ftabk) ? 0u : (uint32_t)a.v.ftabk_chars;   // counters follow the reference's op sequence
 	const uint32_t fc = (uint32_t)a.v.ftab_chars;
+	const unsigned long long* w8 = COUNT ? nullptr : reinterpret_cast<const unsigned long long*>(a.v.walk8);
 	ReadRegs<RW> rd;
 	uint64_t top = 0, bot = 0, fi = 0;
-	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0;
+	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0, slow_until = 0;
 	int mode = M_NEED;
 	unsigned long long c_ps = 0, c_ft = 0, c_sides = 0, c_lf = 0;
 	WarpPool pool; pool.base = pool.end = 0;
@@ -677,7 +707,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 						const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
 						nh = 0; rlen = a.b.len[mate][unit];
 						if(!((fl >> mate) & 1) || rlen == 0) a.nhits[tid] = 0;          // filtered mate: stays M_NEED
-						else { rd.load(a.pk + (size_t)tid * a.W, a.nm + (size_t)tid * a.W, a.W); cur = 0; start_search(); }
+						else { rd.load(a.pk + (size_t)tid * a.W, a.nm + (size_t)tid * a.W, a.W); cur = 0; slow_until = 0; start_search(); }
 					} else mode = M_DONE;
 				}
 				if(__any_sync(0xffffffffu, want && !got)) more = false;      // global counter ran past the end
@@ -688,16 +718,19 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 		int c = 4;
 		ulonglong2 e = make_ulonglong2(0, 0), tq = e, bq = e;
 		const bool lf = mode == M_LF;
-		bool range = false;
+		bool range = false, jump = false;
 		if(mode == M_FTAB) e = __ldg(ftab2 + fi);                           // (top, bot) of the 10-mer: one request
 		else if(mode == M_FTABK) e = __ldg(ftabk + fi);                     // (top, bot) of the K-mer
 		else if(lf) {
 			c = rd.base(dep);
 			if(c <= 3) {
 				range = (bot - top) != 1;
-				tq = __ldg(r16 + (top >> 6) * 4 + c);                       // (occ, bits): one request per rank query
-				bq = tq;
-				if(range && (bot >> 6) != (top >> 6)) bq = __ldg(r16 + (bot >> 6) * 4 + c);
+				if(!range && w8 && dep >= slow_until && rlen - dep >= 8) { jump = true; e.x = __ldg(w8 + top); }   // eight single-row steps in one gather
+				else {
+					tq = __ldg(r16 + (top >> 6) * 4 + c);                   // (occ, bits): one request per rank query
+					bq = tq;
+					if(range && (bot >> 6) != (top >> 6)) bq = __ldg(r16 + (bot >> 6) * 4 + c);
+				}
 			}
 		}
 		// ---------------- consume ----------------
@@ -717,6 +750,12 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 				if(after_hit(hl)) start_search();
 			} else if(dep < rlen) mode = M_LF;
 			else hit_and_restart();
+		} else if(jump) {
+			uint64_t win; uint32_t nwin; rd.window(dep, win, nwin);
+			if((e.x >> 56) == 8 && !(nwin & 0xffu) && !(((e.x >> 40) ^ win) & 0xffffull)) {
+				top = e.x & kWalkRowMask; bot = top + 1; dep += 8;
+				if(dep >= rlen) hit_and_restart();
+			} else slow_until = dep + 8;                 // one of the next eight steps ends the hit: take them one by one
 		} else if(lf) {
 			bool fail = c > 3;
 			uint64_t t = 0, b = 0;
@@ -1108,6 +1147,35 @@ __global__ void __launch_bounds__(kSearchThreads) k_resolve_c(const ResolveArgs 
 	if(COUNT && gl == 0 && a.ctr) { atomicAdd(&a.ctr->walk_steps, c_walk); atomicAdd(&a.ctr->rows_resolved, c_rows); }
 }
 
+// walk8: for every SA row r the state of eight successive mapLF1 steps (bt2_idx.h:2910): the bases BWT[r0..r7]
+// (2 bits each, first step in the low bits) and the row reached, packed as row | bases << 40 | n_valid << 56.
+// n_valid < 8 when the walk meets the '$' row.  While a search holds a single row and the next eight read
+// bases equal the stored ones, eight dependent rank gathers collapse into this one 8-byte gather.
+// 4 lanes per row (lane j fetches base j's rank16 entry: the 64-byte chunk is one request).
+__global__ void __launch_bounds__(kSearchThreads) k_build_walk8(IndexView v, uint64_t nrows, uint64_t* out) {
+	const unsigned lane = threadIdx.x & 31, gl = lane & 3, gbase = lane & 28, gmask = 0xFu << gbase;
+	const ulonglong2* r16 = reinterpret_cast<const ulonglong2*>(v.rank16);
+	const uint64_t ngroups = (uint64_t)gridDim.x * (kSearchThreads / 4);
+	const uint64_t per = (nrows + ngroups - 1) / ngroups;
+	const uint64_t g = (uint64_t)blockIdx.x * (kSearchThreads / 4) + (threadIdx.x >> 2);
+	// consecutive rows per group keep the first gathers of neighbouring rows in the same 64-row chunk
+	for(uint64_t idx = g * per; idx < min(nrows, (g + 1) * per); idx++) {
+		uint64_t row = idx, chars = 0; uint32_t nv = 0;
+		for(; nv < 8; nv++) {
+			if(row == v.zoff) break;
+			const ulonglong2 e = __ldg(r16 + (row >> 6) * 4 + gl);
+			const uint32_t off = (uint32_t)(row & 63);
+			const uint64_t mine = v.fchr[gl] + (e.x & kOccMask) + (uint64_t)__popcll(e.y & ((1ull << off) - 1ull));
+			const unsigned who = (__ballot_sync(gmask, (e.y >> off) & 1ull) >> gbase) & 0xFu;
+			const int src = __ffs(who) - 1;
+			if(src < 0) break;
+			chars |= (uint64_t)src << (2 * nv);
+			row = __shfl_sync(gmask, mine, gbase + src);
+		}
+		if(gl == 0) out[idx] = (row & kWalkRowMask) | (chars << 40) | ((uint64_t)nv << 56);
+	}
+}
+
 // Resolve by table: the sequence id of every SA row was precomputed at index load (k_resolve_c<.,true>), so
 // resolving a row is one 2- or 4-byte gather instead of a ~8-step dependent walk.
 __global__ void __launch_bounds__(256) k_lookup(const ResolveArgs a) {
@@ -1305,6 +1373,21 @@ extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out)
 					CK(cudaDeviceSynchronize());
 					cudaFree(sc);
 					if(h.wide_sample) v.rtab32 = (const uint32_t*)tab; else v.rtab16 = (const uint16_t*)tab;
+				}
+			}
+			// walk8: eight single-row LF steps per gather, if 8 bytes per row still leave room for the batch buffers
+			{
+				const char* e = getenv("CFB_WALK8");
+				const uint64_t nrows = h.len + 1;
+				cudaMemGetInfo(&free_b, &total_b);
+				if(!(e && e[0] == '0') && nrows < (1ull << 40) && nrows * 8 + (24ull << 30) < free_b) {
+					void* tab = nullptr;
+					CK(cudaMalloc(&tab, nrows * 8 + 16));
+					ix->dptrs.push_back(tab); ix->device_bytes += nrows * 8;
+					int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_build_walk8, kSearchThreads, 0);
+					k_build_walk8<<<prop.multiProcessorCount * std::max(occ, 1) * 4, kSearchThreads>>>(v, nrows, (uint64_t*)tab);
+					CK(cudaDeviceSynchronize());
+					v.walk8 = (const uint64_t*)tab;
 				}
 			}
 		}

@@ -88,6 +88,39 @@ def test_classify_matches_oracle_adversarial(case, adv_base, adv_reads):
     o.close()
 
 
+LAYOUT_VARIANTS = {
+    "no_walk8": {"CFB_WALK8": "0"},
+    "no_tables": {"CFB_WALK8": "0", "CFB_RESOLVE_TABLE": "0", "CFB_FTABK": "10"},
+    "ftabk11": {"CFB_FTABK": "11"},
+    "ftabk12_walk_resolve": {"CFB_FTABK": "12", "CFB_RESOLVE_TABLE": "0"},
+    "coop8": {"CFB_GROUP": "8", "CFB_LEGACY_LAYOUTS": "1"},
+}
+
+
+@pytest.mark.parametrize("variant", sorted(LAYOUT_VARIANTS))
+def test_every_device_layout_gives_the_same_records(variant, adv_base, adv_reads, monkeypatch):
+    """The derived tables (K-mer jump table, resolve table, walk8) and the kernel variants are pure
+    accelerations: with any of them switched off the records are the oracle's as well."""
+    for k, v in LAYOUT_VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
+    reads = util.parse_reads(adv_reads)
+    b = util.Batch([a for _, a in reads])
+    o = util.Oracle(adv_base)
+    on, orec, _ = o.classify(b, util.make_oparams())
+    gn, grec = gpu_classify(adv_base, b)
+    assert_same(on, orec, gn, grec)
+    o.close()
+    base = util.build_index("syn_a", 5, 4, 60000, seed=7, strains=True)
+    seqs = util.synth.make_genomes(5, 4, 60000, 7)
+    o = util.Oracle(base)
+    rd = util.synth.sample_reads(seqs, 6000, 100, seed=77, lens=(30, 300))
+    b = util.Batch([a for _, a in rd])
+    on, orec, _ = o.classify(b, util.make_oparams())
+    gn, grec = gpu_classify(base, b)
+    assert_same(on, orec, gn, grec)
+    o.close()
+
+
 def test_classify_matches_oracle_synthetic_se_pe_mixed():
     base = util.build_index("syn_a", 5, 4, 60000, seed=7, strains=True)
     seqs = util.synth.make_genomes(5, 4, 60000, 7)
