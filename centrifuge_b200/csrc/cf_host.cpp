@@ -657,7 +657,7 @@ struct TextPipe {
 	}
 	~TextPipe() { for(int m = 0; m < 2; m++) for(size_t i = 0; i < buf[m].size(); i++) cfb_host_free(buf[m][i]); }
 	bool init(bool paired) {
-		nslots = cfb_ctx_slots(ctx); cap = 2 * o.text_block + 4096;
+		nslots = std::min(cfb_ctx_slots(ctx), 4); cap = 2 * o.text_block + 4096;     // 4 spans cover reader + 2 on the device + writer
 		for(int m = 0; m < (paired ? 2 : 1); m++) while((int)buf[m].size() < nslots) {
 			unsigned char* p = (unsigned char*)cfb_host_alloc(cap);
 			if(!p) return false;

@@ -411,6 +411,7 @@ struct TextSlot {
 	DBuf<unsigned long long> sp;
 	DBuf<unsigned long long> tscal; HBuf<unsigned long long> h_tscal;    // [0] status [1] maxlen [2] n_multi [3] unused [4],[5] line totals [6] tsv bytes
 	uint64_t n_rec = 0; int n_mates = 1; cfb_text_opts opt; uint64_t bytes[2] = {0, 0}; bool pending = false;
+	uint64_t spec_tsv = 0, spec_multi = 0;      // bytes / tie-set records already copied home behind the kernels
 	void release() {
 		for(int m = 0; m < 2; m++) { d_text[m].release(); h_text[m].release(); nl[m].release(); tile_cnt[m].release(); tile_off[m].release(); seedv[m].release(); seq_off[m].release(); qual_off[m].release(); }
 		tbsum.release(); name_off.release(); name_len.release(); id_len.release(); row_bytes.release(); sec.release(); txt_off.release(); sel.release(); num.release();
@@ -424,6 +425,7 @@ struct TextCtx {
 	std::vector<uint64_t> h_sp_taxid;
 	FmtTables tb;
 	uint32_t maxlen_hint = 128;
+	double tsv_ratio = 64.0, multi_ratio = 0.05;     // bytes / tie sets per unit seen so far (size the speculative D2H)
 	TextSlot slots[kSlots - 1];
 	void release() {
 		nd_taxid.release(); nd_info.release(); sp_taxid.release(); sn_off.release(); sn_blob.release(); rk_off.release(); rk_blob.release(); sp_total.release();
@@ -487,6 +489,12 @@ static int text_enqueue_format(cfb_ctx* c, Slot& s, TextSlot& t) {
 	k_scan_apply<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(t.row_bytes.p, n, s.bsum.p, (const uint64_t*)(t.tscal.p + 6), t.txt_off.p);
 	k_fmt_write<<<ublocks, 128, 0, s.st>>>(fa);
 	c->launches += 5;
+	// rows and tie sets follow the kernels home at the size earlier spans suggest; cfb_text_wait fetches a remainder if any
+	t.spec_tsv = std::min<uint64_t>(t.d_tsv.cap, (uint64_t)((double)n * tc.tsv_ratio * 1.05) + 4096);
+	t.spec_multi = std::min<uint64_t>(n, (uint64_t)((double)n * tc.multi_ratio * 1.2) + 256);
+	CK(t.h_tsv.ensure(t.spec_tsv + 1)); CK(t.h_multi.ensure(t.spec_multi * stride + 1));
+	CK(cudaMemcpyAsync(t.h_tsv.p, t.d_tsv.p, t.spec_tsv, cudaMemcpyDeviceToHost, s.st));
+	CK(cudaMemcpyAsync(t.h_multi.p, t.multi.p, t.spec_multi * stride * 8, cudaMemcpyDeviceToHost, s.st));
 	CK(cudaMemcpyAsync(t.h_tscal.p, t.tscal.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.st));
 	CK(cudaGetLastError());
 	return CFB_OK;
@@ -574,7 +582,7 @@ extern "C" int cfb_text_submit(cfb_ctx* c, int slot, const void* text_a, uint64_
 	for(int m = 0; m < 2; m++) { s.bv.off[m] = m < nm ? s.d_off.p + m * (n + 1) : nullptr; s.bv.len[m] = m < nm ? s.d_len.p + m * n : nullptr; }
 	s.n_bases = bytes_a + t.bytes[1];
 	if(o->maxlen_hint) tc.maxlen_hint = std::max(tc.maxlen_hint, len_class(o->maxlen_hint));
-	s.maxlen = tc.maxlen_hint;
+	s.maxlen = tc.maxlen_hint; s.want_host = false;
 	rc = text_enqueue_all(c, s, t); if(rc) return rc;
 	s.pending = true; t.pending = true;
 	return CFB_OK;
@@ -608,11 +616,21 @@ extern "C" int cfb_text_wait(cfb_ctx* c, int slot, int discard, cfb_text_result*
 		const uint64_t tsv = t.h_tscal.p[6];
 		if(tsv > t.d_tsv.cap) { CK(t.d_tsv.ensure(tsv + tsv / 8)); rc = text_enqueue_format(c, s, t); if(rc) return rc; continue; }
 		const uint64_t n_multi = t.h_tscal.p[2];
-		CK(t.h_tsv.ensure(tsv + 1));
-		if(tsv) CK(cudaMemcpyAsync(t.h_tsv.p, t.d_tsv.p, tsv, cudaMemcpyDeviceToHost, s.st));
-		if(n_multi) { CK(t.h_multi.ensure(n_multi * out->multi_stride)); CK(cudaMemcpyAsync(t.h_multi.p, t.multi.p, n_multi * out->multi_stride * 8, cudaMemcpyDeviceToHost, s.st)); }
+		tc.tsv_ratio = std::max(tc.tsv_ratio * 0.98, (double)tsv / (double)t.n_rec);
+		tc.multi_ratio = std::max(tc.multi_ratio * 0.98, (double)n_multi / (double)t.n_rec);
+		bool more = false;
+		if(tsv > t.spec_tsv) {
+			if(tsv + 1 > t.h_tsv.cap) { CK(t.h_tsv.ensure(tsv + 1)); CK(cudaMemcpyAsync(t.h_tsv.p, t.d_tsv.p, tsv, cudaMemcpyDeviceToHost, s.st)); }
+			else CK(cudaMemcpyAsync(t.h_tsv.p + t.spec_tsv, t.d_tsv.p + t.spec_tsv, tsv - t.spec_tsv, cudaMemcpyDeviceToHost, s.st));
+			more = true;
+		}
+		if(n_multi > t.spec_multi) {
+			CK(t.h_multi.ensure(n_multi * out->multi_stride + 1));
+			CK(cudaMemcpyAsync(t.h_multi.p, t.multi.p, n_multi * out->multi_stride * 8, cudaMemcpyDeviceToHost, s.st));
+			more = true;
+		}
 		if(!discard) { const uint32_t nsp3 = 3 * tc.tb.n_sp; k_sp_commit<<<(nsp3 + 255) / 256, 256, 0, s.st>>>(t.sp.p, tc.sp_total.p, nsp3); c->launches++; }
-		CK(cudaStreamSynchronize(s.st));
+		if(more) CK(cudaStreamSynchronize(s.st));
 		out->tsv = t.h_tsv.p; out->tsv_bytes = tsv; out->multi = (const uint64_t*)t.h_multi.p; out->n_multi = n_multi;
 		return CFB_OK;
 	}

@@ -828,7 +828,8 @@ __device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, Unit
 	return u.n_mates > 0;
 }
 
-__global__ void __launch_bounds__(128) k_prep(const UnitArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
 	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
 	if(unit >= a.b.n_units) return;
 	UnitHits u; const uint8_t* fw[2];
@@ -863,7 +864,8 @@ __global__ void __launch_bounds__(128) k_rows(const UnitArgs a) {
 	for_each_visit(a.p, u, er);
 }
 
-__global__ void __launch_bounds__(128) k_score(const UnitArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_score(const UnitArgs a) {
 	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
 	if(unit >= a.b.n_units) return;
 	uint32_t no = 0;
@@ -1431,7 +1433,7 @@ extern "C" void cfb_params_default(cfb_params* p) {
 }
 
 // ---------------------------------------------------------------------------------------
-static const int kSlots = 5;   // 4 pipelined slots + 1 for resident batches
+static const int kSlots = 9;   // 8 pipelined slots + 1 for resident batches
 
 struct Slot {
 	cudaStream_t st = nullptr;
@@ -1450,6 +1452,7 @@ struct Slot {
 	// batch bookkeeping
 	BatchView bv; uint64_t n_units = 0, n_bases = 0; uint32_t maxlen = 0, cap = 0; uint64_t rows_cap = 0, dense_cap = 0;
 	bool pending = false, reran = false;
+	bool want_host = false; uint64_t d2h_recs = 0;     // records already copied to h_recs by the speculative D2H queued behind the kernels
 	void release() {
 		h_bases.release(); h_off.release(); h_len.release(); h_flags.release(); d_bases.release(); d_off.release(); d_len.release(); d_flags.release();
 		pk.release(); nm.release(); hits.release(); nhits.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
@@ -1472,6 +1475,7 @@ struct cfb_ctx {
 	uint64_t launches = 0;
 	int search_blocks = 0, resolve_blocks = 0, group = 1; int resolve_mode = 2;   // 0 = 8-lane sides, 1 = thread/blocks, 2 = 4-lane rank16
 	cfb_dbatch resident; bool resident_used = false;
+	double rec_ratio = 2.0;       // records per unit seen so far (sizes the speculative D2H)
 	TextCtx* text = nullptr;
 };
 
@@ -1663,7 +1667,8 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 		search_kernel(variant, c->count)<<<blocks, kSearchThreads, 0, s.st>>>(sa);
 		c->launches++;
 		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
-		k_prep<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
+		k_prep<7><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;          // <= 72 registers
+
 		k_scan_sums<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nrows.p, n, s.bsum.p);
 		k_scan_top<<<1, 1024, 0, s.st>>>(s.bsum.p, scan_blocks, (uint64_t*)(s.scal.p + 3));
 		k_scan_apply<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nrows.p, n, s.bsum.p, (const uint64_t*)(s.scal.p + 3), s.row_off.p);
@@ -1679,13 +1684,23 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	else { if(c->count) k_resolve<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
 	c->launches++;
 	if(time_it) CK(cudaEventRecord(s.ev[3], s.st));
-	k_score<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
+	k_score<12><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;           // <= 40 registers: occupancy beats the few spills (measured)
 	k_scan_sums<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nout.p, n, s.bsum.p);
 	k_scan_top<<<1, 1024, 0, s.st>>>(s.bsum.p, scan_blocks, (uint64_t*)(s.scal.p + 4));
 	k_scan_apply<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nout.p, n, s.bsum.p, (const uint64_t*)(s.scal.p + 4), s.out_off.p);
 	k_compact<<<(unsigned)((n + 1 + 127) / 128), 128, 0, s.st>>>((uint32_t)n, s.row_off.p, s.out_off.p, s.sparse.p, s.dense.p, s.rec_off32.p, s.dense_cap, (unsigned int*)(s.scal.p + 2));
 	c->launches += 4;
 	if(time_it) CK(cudaEventRecord(s.ev[4], s.st));
+	s.d2h_recs = 0;
+	if(s.want_host) {
+		// results go home behind the kernels without waiting for the host to learn their size: record offsets
+		// exactly, records for the count the previous batches suggest (finish_batch fetches a remainder if any)
+		const uint64_t guess = std::min<uint64_t>(s.dense_cap, (uint64_t)((double)n * c->rec_ratio * 1.05) + 4096);
+		CK(s.h_recs.ensure(guess + 1)); CK(s.h_rec_off.ensure(n + 1));
+		CK(cudaMemcpyAsync(s.h_rec_off.p, s.rec_off32.p, (n + 1) * 4, cudaMemcpyDeviceToHost, s.st));
+		CK(cudaMemcpyAsync(s.h_recs.p, s.dense.p, guess * sizeof(OutRec), cudaMemcpyDeviceToHost, s.st));
+		s.d2h_recs = guess;
+	}
 	CK(cudaMemcpyAsync(s.h_scal.p, s.scal.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.st));
 	CK(cudaGetLastError());
 	return CFB_OK;
@@ -1713,10 +1728,16 @@ static int finish_batch(cfb_ctx* c, Slot& s, bool time_it, bool to_host, cfb_res
 	}
 	const uint64_t nrec = s.h_scal.p[4];
 	if(to_host) {
-		CK(s.h_recs.ensure(nrec + 1)); CK(s.h_rec_off.ensure(s.n_units + 1));
-		CK(cudaMemcpyAsync(s.h_rec_off.p, s.rec_off32.p, (s.n_units + 1) * 4, cudaMemcpyDeviceToHost, s.st));
-		if(nrec) CK(cudaMemcpyAsync(s.h_recs.p, s.dense.p, nrec * sizeof(OutRec), cudaMemcpyDeviceToHost, s.st));
-		CK(cudaStreamSynchronize(s.st));
+		if(s.n_units) c->rec_ratio = std::max(c->rec_ratio * 0.98, (double)nrec / (double)s.n_units);
+		if(!s.want_host || nrec > s.d2h_recs) {       // not (fully) covered by the speculative copy
+			const uint64_t have = s.want_host ? s.d2h_recs : 0;
+			if(nrec + 1 > s.h_recs.cap) {             // grow, keeping nothing: copy everything again
+				CK(s.h_recs.ensure(nrec + 1));
+				if(nrec) CK(cudaMemcpyAsync(s.h_recs.p, s.dense.p, nrec * sizeof(OutRec), cudaMemcpyDeviceToHost, s.st));
+			} else if(nrec > have) CK(cudaMemcpyAsync(s.h_recs.p + have, s.dense.p + have, (nrec - have) * sizeof(OutRec), cudaMemcpyDeviceToHost, s.st));
+			if(!s.want_host) { CK(s.h_rec_off.ensure(s.n_units + 1)); CK(cudaMemcpyAsync(s.h_rec_off.p, s.rec_off32.p, (s.n_units + 1) * 4, cudaMemcpyDeviceToHost, s.st)); }
+			CK(cudaStreamSynchronize(s.st));
+		}
 	}
 	if(out) { out->n_units = s.n_units; out->n_recs = nrec; out->rec_off = s.h_rec_off.p; out->recs = reinterpret_cast<const cfb_rec*>(s.h_recs.p); }
 	return CFB_OK;
@@ -1728,7 +1749,7 @@ extern "C" int cfb_classify_submit(cfb_ctx* c, int slot, const cfb_batch* b) {
 	Slot& s = c->slots[slot];
 	if(s.pending) return fail(CFB_EINVAL, "slot %d still has an un-waited batch", slot);
 	int rc = stage_batch(c, s, b); if(rc) return rc;
-	s.cap = 0;
+	s.cap = 0; s.want_host = true;
 	rc = enqueue_kernels(c, s, 0, false); if(rc) return rc;
 	s.pending = true;
 	return CFB_OK;
