@@ -257,34 +257,34 @@ struct Species {
 
 typedef std::map<std::vector<uint64_t>, uint64_t, IdsLess> Observed;
 
-static void em_step(const Observed& observed, const std::map<uint64_t, std::vector<uint64_t> >& anc, const std::map<uint64_t, uint64_t>& t2n,
-                    const std::vector<double>& p, std::vector<double>& pn, const std::vector<size_t>& len) {   // aln_sink.h:196-272
+// The EM works on a flattened copy of `observed`: for every key, in map order, the species slots its ids
+// contribute to, in the order the reference's nested loops visit them (aln_sink.h:196-272: the id itself when it
+// is a leaf slot, else its leaf descendants in ascending taxid).  Sums run in that order, so every double is the
+// reference's.  The same arrays drive the device version (cfb_em_abundance).
+struct EmFlat {
+	std::vector<uint64_t> count; std::vector<uint64_t> key_off; std::vector<uint32_t> target;   // K, K+1, T
+	std::vector<uint64_t> len;                                                                    // n
+};
+static void em_step(const EmFlat& f, const std::vector<double>& p, std::vector<double>& pn) {   // aln_sink.h:196-272
 	std::fill(pn.begin(), pn.end(), 0.0);
-	for(Observed::const_iterator it = observed.begin(); it != observed.end(); ++it) {
-		const std::vector<uint64_t>& ids = it->first; const uint64_t count = it->second;
+	const size_t K = f.count.size();
+	for(size_t k = 0; k < K; k++) {
 		double psum = 0.0;
-		for(size_t i = 0; i < ids.size(); i++) {
-			std::map<uint64_t, uint64_t>::const_iterator id = t2n.find(ids[i]);
-			if(id != t2n.end()) { psum += p[id->second]; continue; }
-			std::map<uint64_t, std::vector<uint64_t> >::const_iterator a = anc.find(ids[i]);
-			if(a == anc.end()) continue;
-			for(size_t c = 0; c < a->second.size(); c++) { std::map<uint64_t, uint64_t>::const_iterator ci = t2n.find(a->second[c]); if(ci != t2n.end()) psum += p[ci->second]; }
-		}
+		for(uint64_t t = f.key_off[k]; t < f.key_off[k + 1]; t++) psum += p[f.target[t]];
 		if(psum == 0.0) continue;
-		for(size_t i = 0; i < ids.size(); i++) {
-			std::map<uint64_t, uint64_t>::const_iterator id = t2n.find(ids[i]);
-			if(id != t2n.end()) { pn[id->second] += (count * (p[id->second] / psum)); continue; }
-			std::map<uint64_t, std::vector<uint64_t> >::const_iterator a = anc.find(ids[i]);
-			if(a == anc.end()) continue;
-			for(size_t c = 0; c < a->second.size(); c++) { std::map<uint64_t, uint64_t>::const_iterator ci = t2n.find(a->second[c]); if(ci != t2n.end()) pn[ci->second] += (count * (p[ci->second] / psum)); }
-		}
+		const uint64_t count = f.count[k];
+		for(uint64_t t = f.key_off[k]; t < f.key_off[k + 1]; t++) { const uint32_t j = f.target[t]; pn[j] += (count * (p[j] / psum)); }
 	}
 	double sum = 0.0;
-	for(size_t i = 0; i < pn.size(); i++) sum += (pn[i] / len[i]);
-	for(size_t i = 0; i < pn.size(); i++) pn[i] = pn[i] / len[i] / sum;
+	for(size_t i = 0; i < pn.size(); i++) sum += (pn[i] / f.len[i]);
+	for(size_t i = 0; i < pn.size(); i++) pn[i] = pn[i] / f.len[i] / sum;
 }
 
-static void calc_abundance(const HostIndex& h, Species& sp, size_t& iters, double& last_diff) {   // aln_sink.h:274-495
+extern "C" int cfb_em_abundance(int device, uint64_t n, uint64_t K, const uint64_t* count, const uint64_t* key_off, const uint32_t* target,
+                                const uint64_t* len, double* p, uint64_t* iters, double* last_diff);
+extern "C" const char* cfb_em_last_error(void);
+
+static void calc_abundance(const HostIndex& h, Species& sp, size_t& iters, double& last_diff, int device) {   // aln_sink.h:274-495
 	std::set<uint64_t> leaves;
 	for(Observed::const_iterator it = sp.observed.begin(); it != sp.observed.end(); ++it)
 		for(size_t i = 0; i < it->first.size(); i++) { const TaxNode* n = h.find_node(it->first[i]); if(n && n->leaf) leaves.insert(n->taxid); }
@@ -305,38 +305,61 @@ static void calc_abundance(const HostIndex& h, Species& sp, size_t& iters, doubl
 			}
 			std::sort(ch.begin(), ch.end());
 		}
-	std::map<uint64_t, uint64_t> t2n; std::vector<double> p; std::vector<size_t> len;
+	std::map<uint64_t, uint64_t> t2n; std::vector<double> p; EmFlat f;
 	for(Observed::const_iterator it = sp.observed.begin(); it != sp.observed.end(); ++it) {
 		const std::vector<uint64_t>& ids = it->first; const uint64_t count = it->second;
 		for(size_t i = 0; i < ids.size(); i++) {
 			const uint64_t tid = ids[i];
 			if(!leaves.count(tid)) continue;
-			std::map<uint64_t, uint64_t>::iterator f = t2n.find(tid);
-			if(f == t2n.end()) {
+			std::map<uint64_t, uint64_t>::iterator fnd = t2n.find(tid);
+			if(fnd == t2n.end()) {
 				t2n[tid] = p.size(); p.push_back(1.0 / ids.size() * count);
 				std::map<uint64_t, uint64_t>::const_iterator s = h.sizes.find(tid);
-				len.push_back(s != h.sizes.end() ? (size_t)s->second : std::numeric_limits<size_t>::max());
-			} else p[f->second] += (1.0 / ids.size() * count);
+				f.len.push_back(s != h.sizes.end() ? s->second : (uint64_t)std::numeric_limits<size_t>::max());
+			} else p[fnd->second] += (1.0 / ids.size() * count);
 		}
 	}
-	{ double sum = 0.0; for(size_t i = 0; i < p.size(); i++) sum += (p[i] / len[i]); for(size_t i = 0; i < p.size(); i++) p[i] = (p[i] / len[i]) / sum; }
-	std::vector<double> pn(p.size()), pn2(p.size()), pr(p.size()), pv(p.size());
-	size_t it = 0; double diff = 0.0;
-	for(;;) {
-		em_step(sp.observed, anc, t2n, p, pn, len);
-		em_step(sp.observed, anc, t2n, pn, pn2, len);
-		double ssr = 0.0, ssv = 0.0;
-		for(size_t i = 0; i < p.size(); i++) { pr[i] = pn[i] - p[i]; ssr += pr[i] * pr[i]; pv[i] = pn2[i] - pn[i] - pr[i]; ssv += pv[i] * pv[i]; }
-		if(ssv > 0.0) {
-			const double g = -sqrt(ssr / ssv);
-			for(size_t i = 0; i < p.size(); i++) pn2[i] = std::max(0.0, p[i] - 2 * g * pr[i] + g * g * pv[i]);
-			em_step(sp.observed, anc, t2n, pn2, pn, len);
+	{ double sum = 0.0; for(size_t i = 0; i < p.size(); i++) sum += (p[i] / f.len[i]); for(size_t i = 0; i < p.size(); i++) p[i] = (p[i] / f.len[i]) / sum; }
+	f.key_off.push_back(0);
+	for(Observed::const_iterator it = sp.observed.begin(); it != sp.observed.end(); ++it) {
+		const std::vector<uint64_t>& ids = it->first;
+		for(size_t i = 0; i < ids.size(); i++) {
+			std::map<uint64_t, uint64_t>::const_iterator id = t2n.find(ids[i]);
+			if(id != t2n.end()) { f.target.push_back((uint32_t)id->second); continue; }
+			std::map<uint64_t, std::vector<uint64_t> >::const_iterator a = anc.find(ids[i]);
+			if(a == anc.end()) continue;
+			for(size_t c = 0; c < a->second.size(); c++) { std::map<uint64_t, uint64_t>::const_iterator ci = t2n.find(a->second[c]); if(ci != t2n.end()) f.target.push_back((uint32_t)ci->second); }
 		}
-		diff = 0.0;
-		for(size_t i = 0; i < p.size(); i++) diff += (p[i] > pn[i] ? p[i] - pn[i] : pn[i] - p[i]);
-		if(diff < 0.0000000001) break;
-		if(++it >= 10000) break;
-		p = pn;
+		f.count.push_back(it->second); f.key_off.push_back(f.target.size());
+	}
+	// large problems (or CFB_GPU_EM=1) iterate on the device: same operations in the same order, same doubles
+	const char* ge = getenv("CFB_GPU_EM");
+	const bool on_device = device >= 0 && !p.empty() && ((ge && ge[0] == '1') || (!(ge && ge[0] == '0') && f.target.size() >= (1u << 18)));
+	size_t it = 0; double diff = 0.0;
+	if(on_device) {
+		uint64_t iters64 = 0;
+		if(cfb_em_abundance(device, p.size(), f.count.size(), f.count.data(), f.key_off.data(), f.target.data(), f.len.data(), p.data(), &iters64, &diff) != CFB_OK) {
+			std::cerr << "Error: " << cfb_em_last_error() << std::endl; throw 1;
+		}
+		it = (size_t)iters64;
+	} else {
+		std::vector<double> pn(p.size()), pn2(p.size()), pr(p.size()), pv(p.size());
+		for(;;) {
+			em_step(f, p, pn);
+			em_step(f, pn, pn2);
+			double ssr = 0.0, ssv = 0.0;
+			for(size_t i = 0; i < p.size(); i++) { pr[i] = pn[i] - p[i]; ssr += pr[i] * pr[i]; pv[i] = pn2[i] - pn[i] - pr[i]; ssv += pv[i] * pv[i]; }
+			if(ssv > 0.0) {
+				const double g = -sqrt(ssr / ssv);
+				for(size_t i = 0; i < p.size(); i++) pn2[i] = std::max(0.0, p[i] - 2 * g * pr[i] + g * g * pv[i]);
+				em_step(f, pn2, pn);
+			}
+			diff = 0.0;
+			for(size_t i = 0; i < p.size(); i++) diff += (p[i] > pn[i] ? p[i] - pn[i] : pn[i] - p[i]);
+			if(diff < 0.0000000001) break;
+			if(++it >= 10000) break;
+			p = pn;
+		}
 	}
 	iters = it; last_diff = diff;
 	sp.abundance_len.clear();
@@ -777,12 +800,12 @@ struct TextPipe {
 	}
 };
 
-static void write_report(const HostIndex& h, const Options& o, Species& sp) {   // centrifuge.cpp:3231-3319
+static void write_report(const HostIndex& h, const Options& o, Species& sp, int device) {   // centrifuge.cpp:3231-3319
 	std::cerr << "report file " << o.report << std::endl;
 	std::ofstream ro(o.report.c_str());
 	if(o.abundance) {
 		size_t iters = 0; double diff = 0.0;
-		calc_abundance(h, sp, iters, diff);
+		calc_abundance(h, sp, iters, diff, device);
 		std::cerr << "Number of iterations in EM algorithm: " << iters << std::endl;
 		std::cerr << "Probability diff. (P - P_prev) in the last iteration: " << diff << std::endl;
 	}
@@ -1042,7 +1065,7 @@ extern "C" int cfb_run(int argc, const char** argv) {
 			std::cerr << "[cfb] text pipeline " << tstats.t_total << " s: reader busy " << tstats.t_read << " s, device wait " << tstats.t_gpu_wait << " s, writer busy " << tstats.t_write << " s, submit " << tstats.t_submit << " s, pinned setup " << tstats.t_setup << " s" << std::endl;
 		}
 		if(fo != stdout) fclose(fo); else fflush(stdout);
-		if(!failed && !o.report.empty()) write_report(h, o, sp);
+		if(!failed && !o.report.empty()) write_report(h, o, sp, o.device);
 		if(!failed && kr.enabled()) kr.write();
 		cfb_ctx_destroy(ctx); cfb_index_free(ix);
 		return failed ? 1 : 0;

@@ -219,6 +219,17 @@ int cfb_synth_fasta(const cfb_build_opts* o, const char* path);
  * are rejected with exit code 1 like the reference's getopt table does. */
 int cfb_run(int argc, const char** argv);
 
+/* Abundance EM on the device.  Replaces the iteration of SpeciesMetrics::calculateAbundance
+ * (aln_sink.h:274-495; EM step :196-272, SQUAREM extrapolation :430-470) on a flattened tie-set table:
+ * key k (k < K, in std::map order of `observed`) was seen count[k] times and contributes to the species slots
+ * target[key_off[k] .. key_off[k+1]) in the order the reference's loops visit them; len[j] is the genome size of
+ * slot j; p[0..n) holds the start vector and receives the result.  Every accumulator is summed in the reference's
+ * order without FMA contraction, so the doubles (and the report text) are identical to the CPU iteration.
+ * cfb_run uses it for tables with >= 2^18 contributions (CFB_GPU_EM=1/0 forces it on/off). */
+int cfb_em_abundance(int device, uint64_t n, uint64_t K, const uint64_t* count, const uint64_t* key_off, const uint32_t* target,
+                     const uint64_t* len, double* p, uint64_t* iters, double* last_diff);
+const char* cfb_em_last_error(void);
+
 /* Kraken-style report.  Replaces the `centrifuge-kreport` script (centrifuge-kreport:60-260,
  * default LCA mode; its --show-zeros / --min-score / --min-length options): same bytes from the same classification
  * TSV and index.  cfb_run produces the same report in-process with `--kreport-file F` (plus --kreport-show-zeros,
