@@ -408,6 +408,7 @@ def _main(result):
                      "h2d_bytes_per_step": int(sum(t.nbytes for t in txt)), "d2h_bytes_per_step": int(tsv_bytes // max(a.steps, 1))},
         "gpu_launches": int(launches_value),
         "roofline": {"bound": "hbm", "kernel": "k_search_t", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "random_gather": gather,
+                     "note": "achieved counts the reference algorithm's bytes (SURVEY 8d); jump tables (K-mer table, walk8) skip part of them, so frac can exceed 1: the physical bound is random_gather",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bytes_search), "kernel_ms": 1000 * search_s,
                      "sides_per_read": ctr["sides_search"] / max(ctr["units"], 1), "walk_bytes_per_launch": int(bytes_walk)},
         "kernel_ms": {"search": kms[0] / a.steps, "prep_rows": kms[1] / a.steps, "resolve": kms[2] / a.steps, "score_compact": kms[3] / a.steps, "total": step_ms},

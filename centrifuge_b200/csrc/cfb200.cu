@@ -554,6 +554,9 @@ __global__ void k_build_ftab2(IndexView v, uint64_t n, uint64_t* ftab2) {
 }
 static const uint64_t kOccMask = 0x7fffffffffffffffull;
 static const uint64_t kWalkRowMask = (1ull << 40) - 1ull;   // walk8 entry: row in the low 40 bits
+static const int kJumpRows = 1;                             // widest range advanced through walk8.  Ranges of 2-4 adjacent rows can take the same
+                                                            // jump (LF keeps them adjacent), but on the bench workload they shrink so often that the
+                                                            // failed attempts cost more than the jumps save: 4.44 ms vs 4.25 ms with 1 (measured)
 
 // Extended jump table: the SA range of every K-mer (K > ftabChars), obtained by K - ftabChars LF steps from the
 // 10-mer range -- exactly what partialSearch would compute base by base (hi_aligner.h:985-1008).  It trades
@@ -725,8 +728,13 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 			c = rd.base(dep);
 			if(c <= 3) {
 				range = (bot - top) != 1;
-				if(!range && w8 && dep >= slow_until && rlen - dep >= 8) { jump = true; e.x = __ldg(w8 + top); }   // eight single-row steps in one gather
-				else {
+				if(w8 && (bot - top) <= (uint64_t)kJumpRows && dep >= slow_until && rlen - dep >= 8) {
+					// eight steps in one gather: a single row, or a narrow range whose rows (consecutive walk8 entries, one
+					// or two sectors) all continue with the read's next eight bases -- LF keeps such rows adjacent
+					jump = true; e.x = __ldg(w8 + top); e.y = 0;
+					#pragma unroll
+					for(int i = 1; i < kJumpRows; i++) if(top + i < bot) { const unsigned long long o = __ldg(w8 + top + i); e.y |= (o ^ e.x) >> 40; }   // bases + count must equal entry 0's
+				} else {
 					tq = __ldg(r16 + (top >> 6) * 4 + c);                   // (occ, bits): one request per rank query
 					bq = tq;
 					if(range && (bot >> 6) != (top >> 6)) bq = __ldg(r16 + (bot >> 6) * 4 + c);
@@ -752,8 +760,9 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 			else hit_and_restart();
 		} else if(jump) {
 			uint64_t win; uint32_t nwin; rd.window(dep, win, nwin);
-			if((e.x >> 56) == 8 && !(nwin & 0xffu) && !(((e.x >> 40) ^ win) & 0xffffull)) {
-				top = e.x & kWalkRowMask; bot = top + 1; dep += 8;
+			if((e.x >> 56) == 8 && !e.y && !(nwin & 0xffu) && !(((e.x >> 40) ^ win) & 0xffffull)) {
+				const uint64_t rows = bot - top;
+				top = e.x & kWalkRowMask; bot = top + rows; dep += 8;
 				if(dep >= rlen) hit_and_restart();
 			} else slow_until = dep + 8;                 // one of the next eight steps ends the hit: take them one by one
 		} else if(lf) {
