@@ -949,7 +949,11 @@ extern "C" int cfb_run(int argc, const char** argv) {
 		if(rc || exit_now) return rc;
 		const auto t_start = std::chrono::steady_clock::now();
 		cfb_index* ix = NULL;
-		if(cfb_index_load(o.index.c_str(), o.device, &ix) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; return 1; }
+		// File-to-file runs are bounded by the file system (tens of M reads/s), far below what the plain kernels
+		// deliver (~180 M reads/s), so the tables that buy the last factor of two on the device (resolve table, walk8:
+		// ~0.75 s per Gbp to build) would only delay the first read.  CFB_FULL_TABLES=1 builds them anyway.
+		const uint32_t load_flags = getenv("CFB_FULL_TABLES") ? 0u : (CFB_LOAD_NO_RESOLVE_TABLE | CFB_LOAD_NO_WALK8);
+		if(cfb_index_load_ex(o.index.c_str(), o.device, load_flags, &ix) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; return 1; }
 		cfb_ctx* ctx = NULL;
 		if(cfb_ctx_create(ix, &o.prm, &ctx) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; cfb_index_free(ix); return 1; }
 		const HostIndex& h = *cfb_index_host(ix);

@@ -1297,7 +1297,7 @@ static int upload(cfb_index* ix, const void* src, size_t bytes, const void** dst
 	return CFB_OK;
 }
 
-extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out) {
+extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flags, cfb_index** out) {
 	if(!basename || !out) return fail(CFB_EINVAL, "cfb_index_load: null argument");
 	cfb_index* ix = new cfb_index();
 	std::string err = load_cf_index(basename, ix->h);
@@ -1368,7 +1368,7 @@ extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out)
 			}
 			// resolve table: sequence id of every SA row (walked once here), if it fits comfortably
 			{
-				const char* e = getenv("CFB_RESOLVE_TABLE");
+				const char* e = (flags & CFB_LOAD_NO_RESOLVE_TABLE) ? "0" : getenv("CFB_RESOLVE_TABLE");
 				const uint64_t nrows = h.len + 1, esz = h.wide_sample ? 4 : 2;
 				cudaMemGetInfo(&free_b, &total_b);
 				if(!(e && e[0] == '0') && nrows * esz < free_b / 3) {
@@ -1388,7 +1388,7 @@ extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out)
 			}
 			// walk8: eight single-row LF steps per gather, if 8 bytes per row still leave room for the batch buffers
 			{
-				const char* e = getenv("CFB_WALK8");
+				const char* e = (flags & CFB_LOAD_NO_WALK8) ? "0" : getenv("CFB_WALK8");
 				const uint64_t nrows = h.len + 1;
 				cudaMemGetInfo(&free_b, &total_b);
 				if(!(e && e[0] == '0') && nrows < (1ull << 40) && nrows * 8 + (24ull << 30) < free_b) {
@@ -1408,6 +1408,7 @@ extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out)
 	*out = ix;
 	return CFB_OK;
 }
+extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out) { return cfb_index_load_ex(basename, device, 0u, out); }
 extern "C" void cfb_index_free(cfb_index* ix) {
 	if(!ix) return;
 	if(ix->device >= 0) { cudaSetDevice(ix->device); for(size_t i = 0; i < ix->dptrs.size(); i++) cudaFree(ix->dptrs[i]); }

@@ -42,6 +42,13 @@ typedef struct cfb_ctx   cfb_ctx;     /* per-thread/per-stream work context; not
  * device >= 0 uploads a replica to that GPU; device < 0 loads host tables only
  * (header / taxonomy inspection; classify calls then fail with CFB_ENODEV). */
 int cfb_index_load(const char* basename, int device, cfb_index** out);
+/* Same, with control over the derived device tables that are built at load time (pure accelerations, results are
+ * identical with or without them): the resolve table (sequence id of every SA row, ~0.5 s per Gbp to build) and
+ * walk8 (eight LF steps per gather, ~0.25 s per Gbp).  cfb_run skips both for small inputs, where building them
+ * would cost more than they save. */
+#define CFB_LOAD_NO_RESOLVE_TABLE 1u
+#define CFB_LOAD_NO_WALK8         2u
+int cfb_index_load_ex(const char* basename, int device, uint32_t flags, cfb_index** out);
 void cfb_index_free(cfb_index*);
 
 typedef struct {
