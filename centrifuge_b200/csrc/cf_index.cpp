@@ -66,7 +66,8 @@ struct In {
 };
 }  // namespace
 
-std::string load_cf_index(const std::string& base, HostIndex& ix) {
+std::string load_cf_index(const std::string& base, HostIndex& ix, bool defer_bulk) {
+	ix.bulk_deferred = defer_bulk;
 	// ---------------- .1.cf
 	{
 		In in(base + ".1.cf");
@@ -93,8 +94,8 @@ std::string load_cf_index(const std::string& base, HostIndex& ix) {
 		uint64_t n_frag = in.rd<uint64_t>();
 		if(fseeko(in.f, (off_t)(n_frag * 24), SEEK_CUR) != 0) in.ok = false;       // rstarts[] unused
 		ix.wide_sample = ix.n_pat > 65535;
-		ix.sides.resize(ix.num_sides * ix.side_sz);
-		in.bulk(ix.sides.data(), ix.sides.size());
+		if(defer_bulk) { ix.sides_file_off = (uint64_t)ftello(in.f); if(fseeko(in.f, (off_t)(ix.num_sides * ix.side_sz), SEEK_CUR) != 0) in.ok = false; }
+		else { ix.sides.resize(ix.num_sides * ix.side_sz); in.bulk(ix.sides.data(), ix.sides.size()); }
 		ix.zoff = in.rd<uint64_t>();
 		for(int i = 0; i < 5; i++) ix.fchr[i] = in.rd<uint64_t>();
 		ix.ftab.resize(ix.ftab_len);   in.bulk(ix.ftab.data(), ix.ftab_len * 8);
@@ -106,8 +107,12 @@ std::string load_cf_index(const std::string& base, HostIndex& ix) {
 		In in(base + ".2.cf");
 		if(!in.ok) return "could not open index file " + base + ".2.cf";
 		(void)in.rd<uint32_t>();
-		if(ix.wide_sample) { ix.sample32.resize(ix.offs_len); in.bulk(ix.sample32.data(), ix.offs_len * 4); }
-		else               { ix.sample16.resize(ix.offs_len); in.bulk(ix.sample16.data(), ix.offs_len * 2); }
+		if(defer_bulk) {
+			ix.sample_file_off = (uint64_t)ftello(in.f);
+			if(fseeko(in.f, 0, SEEK_END) != 0 || (uint64_t)ftello(in.f) < ix.sample_file_off + ix.offs_len * (ix.wide_sample ? 4 : 2)) in.ok = false;
+		}
+		else if(ix.wide_sample) { ix.sample32.resize(ix.offs_len); in.bulk(ix.sample32.data(), ix.offs_len * 4); }
+		else                    { ix.sample16.resize(ix.offs_len); in.bulk(ix.sample16.data(), ix.offs_len * 2); }
 		if(!in.ok) return "truncated " + base + ".2.cf";
 	}
 	// ---------------- .3.cf

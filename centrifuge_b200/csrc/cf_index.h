@@ -55,10 +55,13 @@ struct HostIndex {
 	std::vector<int32_t>  seq_path;        // path id per sequence or -1 (taxid not in tree)
 	std::vector<uint64_t> paths;           // n_paths * kPathSlots
 	const TaxNode* find_node(uint64_t taxid) const;
+	// load_cf_index(.., defer_bulk = true) leaves `sides` and the SA sample on disk and records where they are,
+	// so that the device loader can stream them file -> pinned ring -> HBM without a host copy
+	bool bulk_deferred = false; uint64_t sides_file_off = 0, sample_file_off = 0;
 };
 
 // Returns empty string on success, else the error message.
-std::string load_cf_index(const std::string& basename, HostIndex& out);
+std::string load_cf_index(const std::string& basename, HostIndex& out, bool defer_bulk = false);
 
 }  // namespace cfb
 #endif

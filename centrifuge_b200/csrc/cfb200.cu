@@ -5,6 +5,10 @@
 #include "cf_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <fcntl.h>
+#include <unistd.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1297,10 +1301,48 @@ static int upload(cfb_index* ix, const void* src, size_t bytes, const void** dst
 	return CFB_OK;
 }
 
+// file[off, off+bytes) -> device memory through a ring of pinned buffers: parallel preads fill one buffer while
+// the previous one is on its way over PCIe.  No host copy of the array is kept.
+static int stream_to_device(cfb_index* ix, const std::string& path, uint64_t off, uint64_t bytes, const void** dst) {
+	void* d = nullptr;
+	CK(cudaMalloc(&d, bytes ? bytes + 64 : 64));
+	ix->dptrs.push_back(d); ix->device_bytes += bytes; *dst = d;
+	if(bytes == 0) return CFB_OK;
+	const int fd = open(path.c_str(), O_RDONLY);
+	if(fd < 0) return fail(CFB_EIO, "could not open %s", path.c_str());
+	const size_t kBuf = 64u << 20; const int kRing = 3, kThreads = 8;
+	uint8_t* hb[kRing] = {nullptr, nullptr, nullptr}; cudaEvent_t ev[kRing]; cudaStream_t st = nullptr;
+	int rc = CFB_OK;
+	for(int i = 0; i < kRing; i++) { if(cudaMallocHost((void**)&hb[i], kBuf) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) rc = fail(CFB_ENOMEM, "pinned staging buffers"); }
+	if(rc == CFB_OK && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc = fail(CFB_ECUDA, "stream");
+	uint64_t done = 0; int k = 0;
+	while(rc == CFB_OK && done < bytes) {
+		const size_t n = (size_t)std::min<uint64_t>(kBuf, bytes - done);
+		const int b = k % kRing;
+		if(k >= kRing && cudaEventSynchronize(ev[b]) != cudaSuccess) { rc = fail(CFB_ECUDA, "event"); break; }
+		std::atomic<bool> bad(false);
+		auto piece = [&](int t) {
+			const size_t lo = n * t / kThreads, hi = n * (t + 1) / kThreads; size_t got = lo;
+			while(got < hi) { const ssize_t r = pread(fd, hb[b] + got, hi - got, (off_t)(off + done + got)); if(r <= 0) { bad = true; return; } got += (size_t)r; }
+		};
+		std::vector<std::thread> th;
+		for(int t = 1; t < kThreads; t++) th.emplace_back(piece, t);
+		piece(0);
+		for(size_t t = 0; t < th.size(); t++) th[t].join();
+		if(bad) { rc = fail(CFB_EIO, "short read in %s", path.c_str()); break; }
+		if(cudaMemcpyAsync((uint8_t*)d + done, hb[b], n, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaEventRecord(ev[b], st) != cudaSuccess) { rc = fail(CFB_ECUDA, "H2D of %s", path.c_str()); break; }
+		done += n; k++;
+	}
+	if(st) { if(cudaStreamSynchronize(st) != cudaSuccess && rc == CFB_OK) rc = fail(CFB_ECUDA, "H2D of %s", path.c_str()); cudaStreamDestroy(st); }
+	for(int i = 0; i < kRing; i++) { if(hb[i]) cudaFreeHost(hb[i]); cudaEventDestroy(ev[i]); }
+	close(fd);
+	return rc;
+}
+
 extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flags, cfb_index** out) {
 	if(!basename || !out) return fail(CFB_EINVAL, "cfb_index_load: null argument");
 	cfb_index* ix = new cfb_index();
-	std::string err = load_cf_index(basename, ix->h);
+	std::string err = load_cf_index(basename, ix->h, /*defer_bulk=*/device >= 0);
 	if(!err.empty()) { delete ix; return fail(CFB_EIO, "%s", err.c_str()); }
 	const HostIndex& h = ix->h;
 	ix->device = device;
@@ -1315,8 +1357,10 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 		IndexView& v = ix->view; memset(&v, 0, sizeof v);
 		int rc;
 		#define UP(field, vec, T) if((rc = upload(ix, (vec).data(), (vec).size() * sizeof(T), (const void**)&v.field)) != CFB_OK) { cfb_index_free(ix); return rc; }
-		UP(sides, h.sides, uint8_t) UP(ftab, h.ftab, uint64_t) UP(eftab, h.eftab, uint64_t)
-		if(h.wide_sample) { UP(sample32, h.sample32, uint32_t) } else { UP(sample16, h.sample16, uint16_t) }
+		if((rc = stream_to_device(ix, std::string(basename) + ".1.cf", h.sides_file_off, h.num_sides * h.side_sz, (const void**)&v.sides)) != CFB_OK) { cfb_index_free(ix); return rc; }
+		UP(ftab, h.ftab, uint64_t) UP(eftab, h.eftab, uint64_t)
+		if((rc = stream_to_device(ix, std::string(basename) + ".2.cf", h.sample_file_off, h.offs_len * (h.wide_sample ? 4 : 2),
+		                          h.wide_sample ? (const void**)&v.sample32 : (const void**)&v.sample16)) != CFB_OK) { cfb_index_free(ix); return rc; }
 		UP(brow, h.brow, uint64_t) UP(bseq, h.bseq, uint32_t) UP(bbits, h.bbits, uint32_t)
 		UP(seq_taxid, h.seq_taxid, uint64_t) UP(seq_path, h.seq_path, int32_t) UP(paths, h.paths, uint64_t)
 		#undef UP
