@@ -97,6 +97,34 @@ def write_fastq(path, codes, prefix="r"):
             f.write(b"@%s%d\n" % (prefix.encode(), i) + asc[i].tobytes() + b"\n+\n" + q + b"\n")
 
 
+def bind_to_gpu_numa_node(dev):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it allocates
+    (first touch) and the threads that fill them are local to that GPU's PCIe root.  Best effort."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(dev)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # sysfs uses 4-digit domains
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons during the timed regions, via NVML in-process (no nvidia-smi forks, which
     contend for the driver lock with the CUDA calls being timed)."""
@@ -235,6 +263,7 @@ def _main(result):
                           "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=result, flush=True)
         return 0
 
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     import torch
     from centrifuge_b200 import capi
     if not torch.cuda.is_available():
@@ -416,7 +445,12 @@ def _main(result):
         "taxon_vector": {"len": int(counts.numel()), "classified_reads_rank0": int(local_counts[:-1, 0].sum()), "unclassified_reads_rank0": int(local_counts[-1, 1])},
         "wall_s_value_region": wall_s,
     }
-    if rank == 0:
+    if numa is not None:
+        out["config"]["numa_node"] = numa
+    if rank == 0 and world > 1:
+        out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": "reported by the N=1 run only"}
+        print(json.dumps(out), file=result, flush=True)
+    elif rank == 0:
         # bounded CPU baseline: the unmodified reference binary on the host cores
         try:
             arm = RefArm(a, base, d, local)
