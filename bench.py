@@ -255,7 +255,7 @@ def _main(result):
         val = nreads / tot
         sample = "%d reads per step (bounded sample), centrifuge-class -p %d (best of a thread sweep up to %d), FASTQ in, TSV to /dev/null, index load differenced out" % (
             nreads // a.steps, arm.threads, ncores)
-        print(json.dumps({"metric": "reads/sec (100 bp SE classification)", "value": val, "unit": "reads/s", "n_gpus": a.gpus, "steps": a.steps,
+        print(json.dumps({"metric": "reads/sec (%d bp SE classification)" % a.rdlen, "value": val, "unit": "reads/s", "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": min(a.warmup, 1), "ms_per_step": 1000 * tot / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "u64", "data": "synthetic", "impl": "reference",
                           "config": {"workload": workload, "sample": sample},
@@ -428,7 +428,7 @@ def _main(result):
         gather = {"what": "random 32-byte sector gathers: achieved vs the ceiling measured on this part by tools/gather_bench.cu (~34.5 G sectors/s)",
                   "achieved_gsectors_s": sect / search_s / 1e9, "ceiling_gsectors_s": 34.5, "frac": sect / search_s / 1e9 / 34.5}
     out = {
-        "metric": "reads/sec (100 bp SE classification)", "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "metric": "reads/sec (%d bp SE classification)" % a.rdlen, "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1000 * dev_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload, "index_bytes_hbm": int(ix.info.device_bytes), "l2": "index replica %.0f MB vs 126 MB L2; same batch re-walked every step" % (ix.info.device_bytes / 1e6),
                    "parallelism": "reads sharded over %d GPU(s), index replicated, 1 NCCL all-reduce of per-taxon counts per step" % world},

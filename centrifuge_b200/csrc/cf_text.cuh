@@ -464,7 +464,7 @@ static int text_init(cfb_ctx* c) {
 	return CFB_OK;
 }
 
-static uint32_t len_class(uint32_t maxlen) { return maxlen <= 128 ? 128u : (maxlen <= 320 ? 320u : ((maxlen + 1023u) / 1024u) * 1024u); }
+static uint32_t len_class(uint32_t maxlen) { return maxlen <= 128 ? 128u : (maxlen <= 160 ? 160u : (maxlen <= 320 ? 320u : ((maxlen + 1023u) / 1024u) * 1024u)); }
 
 static int text_enqueue_format(cfb_ctx* c, Slot& s, TextSlot& t) {
 	TextCtx& tc = *c->text;

@@ -803,6 +803,7 @@ typedef void (*SearchKernel)(const SearchArgs);
 static SearchKernel search_kernel(int g, bool count) {
 	switch(g) {
 		case 1: return count ? k_search_t<true, 4> : k_search_t<false, 4>;      // reads up to 128 bases
+		case 101: return count ? k_search_t<true, 5> : k_search_t<false, 5>;    // reads up to 160 bases (2 x 150 bp runs)
 		case 100: return count ? k_search_t<true, 10> : k_search_t<false, 10>;  // reads up to 320 bases
 		case 16: return count ? k_search<true, 1> : k_search<false, 1>;   // generic template at G = 1 (A/B only)
 		case 2: return count ? k_search<true, 2> : k_search<false, 2>;
@@ -1704,8 +1705,8 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 		  k_pack<<<(unsigned)((ntasks * W + 127) / 128), 128, 0, s.st>>>(pa); c->launches++; }
 		sa.task_ctr = (unsigned int*)(s.scal.p + 0); sa.task_ctr64 = s.scal.p + 0; sa.ntasks = (uint32_t)ntasks; sa.overflow = (unsigned int*)(s.scal.p + 2); sa.ctr = ctr;
 		int variant = c->group;
-		if(variant == 1) { if(s.maxlen > 320) variant = 16; else if(s.maxlen > 128) variant = 100; }   // longer reads: wider register window / windowed kernel
-		const bool pooled = variant == 1 || variant == 100;
+		if(variant == 1) { if(s.maxlen > 320) variant = 16; else if(s.maxlen > 160) variant = 100; else if(s.maxlen > 128) variant = 101; }   // longer reads: wider register window / windowed kernel
+		const bool pooled = variant == 1 || variant == 100 || variant == 101;
 		const int lanes = (variant == 16 || pooled) ? 1 : variant;
 		int occ = 1;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel(variant, c->count), kSearchThreads, 0));

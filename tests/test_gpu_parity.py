@@ -121,6 +121,20 @@ def test_every_device_layout_gives_the_same_records(variant, adv_base, adv_reads
     o.close()
 
 
+@pytest.mark.parametrize("lens", [(100, 128), (129, 160), (150, 150), (161, 320), (300, 700)])
+def test_every_read_length_class_matches_oracle(lens):
+    """The search kernel is instantiated per read-length class (register words holding the packed read)."""
+    base = util.build_index("syn_a", 5, 4, 60000, seed=7, strains=True)
+    seqs = util.synth.make_genomes(5, 4, 60000, 7)
+    o = util.Oracle(base)
+    rd = util.synth.sample_reads(seqs, 5000, lens[0], seed=lens[0] + lens[1], lens=lens)
+    b = util.Batch([a for _, a in rd])
+    on, orec, _ = o.classify(b, util.make_oparams())
+    gn, grec = gpu_classify(base, b)
+    assert_same(on, orec, gn, grec)
+    o.close()
+
+
 def test_classify_matches_oracle_synthetic_se_pe_mixed():
     base = util.build_index("syn_a", 5, 4, 60000, seed=7, strains=True)
     seqs = util.synth.make_genomes(5, 4, 60000, 7)
