@@ -5,8 +5,10 @@ A "step" is one pass of the hot path over one batch of synthetic 100 bp single-e
 synthetic genus/species index (SURVEY.md Appendix C recipe) replicated in each GPU's HBM.
 
   value     reads/s with the batch already resident in HBM (kernels only, CUDA events, max over ranks)
-  e2e       reads/s through cfb_classify_submit/wait with HOST buffers: H2D of the reads and D2H of the
-            result records inside the timed region, up to cfb_ctx_slots() batches in flight
+  e2e       reads/s through cfb_classify_submit/wait with HOST buffers: every step's H2D of the reads and D2H of the
+            result records are inside the timed region; a step is cut into sub-batches on half of the context's
+            slots and steps stream (step k+1 is submitted before step k's records are collected)
+  e2e_text  the same from FASTQ bytes to TSV bytes through the text-level operator (cfb_text_submit/wait)
   roofline  k_search: algorithmic bytes (128 B per side touched + 16 B per ftab probe, counted by the
             kernel's own counters in a separate un-timed pass) / its CUDA-event time, vs measured HBM peak
   cpu_baseline   the unmodified reference binary (oracle/_ref/centrifuge-class -p <cores>) on a bounded sample
@@ -346,7 +348,10 @@ def _main(result):
     # ---------------- e2e: host buffers in, host records out.  One step = the same batch, cut into
     # n_slots sub-batches that are submitted back to back (H2D of one overlaps the kernels of another)
     # and then waited for: every step is self-contained, all copies are inside the timed region.
-    nslots = ctx.n_slots
+    # Steps stream: the sub-batches of step k+1 are submitted (to the other half of the slots) before the results of
+    # step k are collected, as a caller with a steady supply of reads would do; every step's copies are inside the
+    # timed region, which ends when the last step's records are in host memory.
+    nslots = max(1, ctx.n_slots // 2)
     m = n // nslots
     sub = []
     offs_sub = capi.pinned_array((m,), np.uint64); offs_sub[:] = np.arange(m, dtype=np.uint64) * np.uint64(a.rdlen)
@@ -354,24 +359,35 @@ def _main(result):
         sub.append(capi.make_batch(bases[sl * m * a.rdlen:(sl + 1) * m * a.rdlen], offs_sub, lens[sl * m:(sl + 1) * m], None, None, flags[sl * m:(sl + 1) * m]))
     n_e2e = m * nslots
 
-    def e2e_step():
+    def e2e_submit(step):
+        for sl in range(nslots):
+            ctx.submit((step % 2) * nslots + sl, sub[sl])
+
+    def e2e_collect(step):
         nr = 0
         for sl in range(nslots):
-            ctx.submit(sl, sub[sl])
-        for sl in range(nslots):
-            nr += ctx.wait(sl, copy=False)[1]
+            nr += ctx.wait((step % 2) * nslots + sl, copy=False)[1]
         return nr
 
-    for _ in range(max(1, min(a.warmup, 2))):          # every slot allocates its buffers before the timed region
-        e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    d2h = 0
-    for s in range(a.steps):
-        d2h += e2e_step() * 24 + (n_e2e + nslots) * 4
+    def e2e_run(steps):
+        nr = 0
+        e2e_submit(0)
+        for s in range(1, steps):
+            e2e_submit(s)
+            nr += e2e_collect(s - 1)
+            if dist:
+                step_counts = counts.clone()
+                dist.all_reduce(step_counts)
+        nr += e2e_collect(steps - 1)
         if dist:
             step_counts = counts.clone()
             dist.all_reduce(step_counts)
+        return nr
+
+    e2e_run(max(2, min(a.warmup, 2)))                  # every slot allocates its buffers before the timed region
+    sync_all()
+    t0 = time.perf_counter()
+    d2h = e2e_run(a.steps) * 24 + a.steps * (n_e2e + nslots) * 4
     sync_all()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -387,24 +403,31 @@ def _main(result):
         pt = capi.pinned_array((fm.size,), np.uint8); pt[:] = fm.reshape(-1)
         txt.append(pt)
 
-    def text_step():
+    def text_submit(step):
+        for sl in range(nslots):
+            ctx.text_submit((step % 2) * nslots + sl, txt[sl], None, m, maxlen_hint=a.rdlen)
+
+    def text_collect(step):
         nb = 0
         for sl in range(nslots):
-            ctx.text_submit(sl, txt[sl], None, m, maxlen_hint=a.rdlen)
-        for sl in range(nslots):
-            r = ctx.text_wait(sl, copy=False)
+            r = ctx.text_wait((step % 2) * nslots + sl, copy=False)
             if r["irregular"]:
                 raise RuntimeError("text operator rejected the synthetic FASTQ")
             nb += r["tsv_bytes"] + r["n_multi"] * 8 * 6
         return nb
 
-    for _ in range(max(1, min(a.warmup, 2))):
-        text_step()
+    def text_run(steps):
+        nb = 0
+        text_submit(0)
+        for s in range(1, steps):
+            text_submit(s)
+            nb += text_collect(s - 1)
+        return nb + text_collect(steps - 1)
+
+    text_run(max(2, min(a.warmup, 2)))
     sync_all()
     t0 = time.perf_counter()
-    tsv_bytes = 0
-    for s in range(a.steps):
-        tsv_bytes += text_step()
+    tsv_bytes = text_run(a.steps)
     sync_all()
     tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if dist:

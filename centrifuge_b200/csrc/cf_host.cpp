@@ -962,7 +962,7 @@ extern "C" int cfb_run(int argc, const char** argv) {
 		if(!fo) { std::cerr << "Error: could not open output file " << o.out << std::endl; return 1; }
 		fputs("readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n", fo);
 		Species sp; Formatter fmt(h, o, sp); KReport kr(h, o);
-		const int nslots = cfb_ctx_slots(ctx);
+		const int nslots = std::min(cfb_ctx_slots(ctx), 4);
 		std::vector<HostBatch> hb(nslots);
 		std::vector<bool> busy(nslots, false);
 		int cur = 0; uint64_t rdid = 0;

@@ -1488,7 +1488,7 @@ extern "C" void cfb_params_default(cfb_params* p) {
 }
 
 // ---------------------------------------------------------------------------------------
-static const int kSlots = 9;   // 8 pipelined slots + 1 for resident batches
+static const int kSlots = 17;  // 16 pipelined slots (two waves of 8 sub-batches keep the copy engines busy across batch boundaries) + 1 for resident batches
 
 struct Slot {
 	cudaStream_t st = nullptr;
