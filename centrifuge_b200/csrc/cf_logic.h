@@ -65,6 +65,15 @@ struct Params {
 
 struct HitRec { uint64_t top, bot; uint32_t bwoff, len; };   // 24 bytes
 
+// A row queued for resolution carries the plan of the scoring pass in its high bits, so that pass reads one
+// contiguous array instead of gathering the hit lists again: the first row of every counted hit has kRowStart set
+// plus the hit length (bits 40..55), the list it came from (mate bit 56, strand bit 57) and kRowSameTs when the hit
+// carries the same time stamp as the previous counted hit.  That happens in the reference when a list loop is left
+// through its `break` (the loop-header ts++ is skipped, classifier.h:283-345) and the next list starts with a counted
+// hit: the second hit then does not add its score to entries the first one touched -- a quirk the output depends on.
+// SA rows need 40 bits.
+static const uint64_t kRowMask = (1ull << 40) - 1ull, kRowStart = 1ull << 63, kRowSameTs = 1ull << 58;
+
 struct Counters {   // algorithmic-operation counters (SURVEY.md section 8d definition)
 	unsigned long long units, partial_searches, ftab_probes, sides_search, walk_steps, rows_resolved, lf_steps, ext_searches;
 };
@@ -403,9 +412,9 @@ struct SortAndCount {   // prep pass: sort each visited list, count rows to reso
 	}
 };
 
-struct EmitRows {       // second pass: write the SA rows to resolve, in consumption order
-	const Params& p; const UnitHits& u; uint64_t* out; uint64_t k;
-	CFB_HD EmitRows(const Params& p_, const UnitHits& u_, uint64_t* o) : p(p_), u(u_), out(o), k(0) {}
+struct CountRows {      // same count as SortAndCount on lists that are already sorted (re-run after a capacity overflow)
+	const Params& p; const UnitHits& u; uint64_t rows;
+	CFB_HD CountRows(const Params& p_, const UnitHits& u_) : p(p_), u(u_), rows(0) {}
 	CFB_HD void operator()(int rdi, int fwi, uint64_t maxG) {
 		const HitRec* L = u.L[rdi][fwi]; const uint32_t n = u.n[rdi][fwi];
 		uint64_t cnt = 0;
@@ -414,7 +423,27 @@ struct EmitRows {       // second pass: write the SA rows to resolve, in consump
 			if(hsize(L[hi]) == 0) continue;
 			const uint64_t nelt = hsize(L[hi]) < maxG ? hsize(L[hi]) : maxG;
 			if(nelt > p.ihits) continue;
-			for(uint64_t e = 0; e < nelt; e++) out[k++] = L[hi].top + e;
+			rows += nelt; cnt += nelt;
+			if(cnt >= maxG) break;
+		}
+	}
+};
+
+struct EmitRows {       // second pass: write the SA rows to resolve, in consumption order, with the scoring plan
+	const Params& p; const UnitHits& u; uint64_t* out; uint64_t k; uint32_t ts, last_ts;
+	CFB_HD EmitRows(const Params& p_, const UnitHits& u_, uint64_t* o) : p(p_), u(u_), out(o), k(0), ts(0), last_ts(0xffffffffu) {}
+	CFB_HD void operator()(int rdi, int fwi, uint64_t maxG) {
+		const HitRec* L = u.L[rdi][fwi]; const uint32_t n = u.n[rdi][fwi];
+		uint64_t cnt = 0;
+		for(uint32_t hi = 0; hi < n; hi++, ts++) {            // ts advances exactly as in the reference's loop header
+			if(L[hi].len <= p.min_hitlen) continue;
+			if(hsize(L[hi]) == 0) continue;
+			const uint64_t nelt = hsize(L[hi]) < maxG ? hsize(L[hi]) : maxG;
+			if(nelt > p.ihits) continue;
+			const uint64_t head = kRowStart | ((uint64_t)(L[hi].len & 0xffffu) << 40) | ((uint64_t)(rdi & 1) << 56) | ((uint64_t)(fwi & 1) << 57)
+			                    | (ts == last_ts ? kRowSameTs : 0ull);
+			last_ts = ts;
+			for(uint64_t e = 0; e < nelt; e++) out[k++] = ((L[hi].top + e) & kRowMask) | (e == 0 ? head : 0ull);
 			cnt += nelt;
 			if(cnt >= maxG) break;
 		}
@@ -442,56 +471,51 @@ CFB_HD bool is_host(const IndexView& v, uint64_t taxid) {
 CFB_HD uint32_t path_size(const Entry& e) { return e.pid < 0 ? 0u : 10u; }
 CFB_HD uint64_t path_at(const IndexView& v, const Entry& e, uint32_t i) { return v.paths[(uint64_t)e.pid * 10 + i]; }
 
-struct ScoreVisit {     // third pass: consume resolved ids, build the hit map
-	const IndexView& v; const Params& p; const UnitHits& u; const uint32_t* ids; uint64_t k;
-	Entry* map; uint32_t nmap; uint32_t ts;
-	CFB_HD ScoreVisit(const IndexView& v_, const Params& p_, const UnitHits& u_, const uint32_t* ids_, Entry* m)
-		: v(v_), p(p_), u(u_), ids(ids_), k(0), map(m), nmap(0), ts(0) {}
-	CFB_HDN void operator()(int rdi, int fwi, uint64_t maxG) {
-		const HitRec* L = u.L[rdi][fwi]; const uint32_t n = u.n[rdi][fwi];
-		uint64_t cnt = 0;
-		for(uint32_t hi = 0; hi < n; hi++, ts++) {
-			if(L[hi].len <= p.min_hitlen) continue;
-			if(hsize(L[hi]) == 0) continue;
-			const uint64_t nelt = hsize(L[hi]) < maxG ? hsize(L[hi]) : maxG;
-			if(nelt > p.ihits) continue;
-			const uint32_t* my = ids + k; k += nelt; cnt += nelt;
-			const uint64_t hl = L[hi].len;
-			const uint32_t sc = (uint32_t)((hl - 15) * (hl - 15));
-			for(uint64_t e = 0; e < nelt; e++) {
-				const uint32_t ref = my[e];
-				bool dup = false;                       // coord_ids de-duplication, first-seen order
-				for(uint64_t q = 0; q < e; q++) if(my[q] == ref) { dup = true; break; }
-				if(dup) continue;
-				uint64_t taxID = ref < v.n_seqs ? v.seq_taxid[ref] : 0;
-				if(v.seq_excluded && ref < v.n_seqs && v.seq_excluded[ref]) continue;
-				// addHitToHitMap classifier.h:982-1050
-				const int32_t pid = ref < v.n_seqs ? v.seq_path[ref] : -1;
-				uint8_t rank = (uint8_t)p.class_rank_slot;
-				if(rank > 0 && pid >= 0) {
-					for(; rank < 10; rank++) { const uint64_t t = v.paths[(uint64_t)pid * 10 + rank]; if(t != 0) { taxID = t; break; } }
-				}
-				uint32_t idx = 0;
-				for(; idx < nmap; ++idx) {
-					const bool same = rank == 0 ? ((uint64_t)ref == map[idx].uniqueID) : (taxID == map[idx].taxID);
-					if(same) {
-						if(map[idx].ts != ts) { map[idx].scores[rdi][fwi] += sc; map[idx].lens[rdi][fwi] += (uint32_t)hl; map[idx].ts = ts; }
-						break;
-					}
-				}
-				if(idx >= nmap) {
-					Entry& n2 = map[nmap++];
-					n2.uniqueID = ref; n2.taxID = taxID;
-					n2.scores[0][0] = n2.scores[0][1] = n2.scores[1][0] = n2.scores[1][1] = 0;
-					n2.lens[0][0] = n2.lens[0][1] = n2.lens[1][0] = n2.lens[1][1] = 0;
-					n2.scores[rdi][fwi] = sc; n2.lens[rdi][fwi] = (uint32_t)hl;
-					n2.score = 0; n2.hitlen = 0; n2.ts = ts; n2.pid = pid; n2.rank = rank;
+// Third pass: consume the resolved ids along the plan carried by the row words, build the hit map
+// (classifier.h:299-345 + addHitToHitMap :982-1050).  Time stamps are non-decreasing along the plan, so "same as the
+// previous hit" (kRowSameTs) reproduces every equality the reference's counter produces.
+CFB_HDN uint32_t score_plan(const IndexView& v, const Params& p, const uint64_t* rows, const uint32_t* ids, uint64_t n, Entry* map) {
+	uint32_t nmap = 0, ts = 0;
+	for(uint64_t k = 0; k < n;) {
+		const uint64_t head = rows[k];
+		if(!(head & kRowSameTs)) ts++;
+		const uint64_t hl = (head >> 40) & 0xffffu; const int rdi = (int)((head >> 56) & 1), fwi = (int)((head >> 57) & 1);
+		uint64_t nelt = 1;
+		while(k + nelt < n && !(rows[k + nelt] & kRowStart)) nelt++;
+		const uint32_t* my = ids + k; k += nelt;
+		const uint32_t sc = (uint32_t)((hl - 15) * (hl - 15));
+		for(uint64_t e = 0; e < nelt; e++) {
+			const uint32_t ref = my[e];
+			bool dup = false;                       // coord_ids de-duplication, first-seen order
+			for(uint64_t q = 0; q < e; q++) if(my[q] == ref) { dup = true; break; }
+			if(dup) continue;
+			uint64_t taxID = ref < v.n_seqs ? v.seq_taxid[ref] : 0;
+			if(v.seq_excluded && ref < v.n_seqs && v.seq_excluded[ref]) continue;
+			const int32_t pid = ref < v.n_seqs ? v.seq_path[ref] : -1;
+			uint8_t rank = (uint8_t)p.class_rank_slot;
+			if(rank > 0 && pid >= 0) {
+				for(; rank < 10; rank++) { const uint64_t t = v.paths[(uint64_t)pid * 10 + rank]; if(t != 0) { taxID = t; break; } }
+			}
+			uint32_t idx = 0;
+			for(; idx < nmap; ++idx) {
+				const bool same = rank == 0 ? ((uint64_t)ref == map[idx].uniqueID) : (taxID == map[idx].taxID);
+				if(same) {
+					if(map[idx].ts != ts) { map[idx].scores[rdi][fwi] += sc; map[idx].lens[rdi][fwi] += (uint32_t)hl; map[idx].ts = ts; }
+					break;
 				}
 			}
-			if(cnt >= maxG) break;
+			if(idx >= nmap) {
+				Entry& n2 = map[nmap++];
+				n2.uniqueID = ref; n2.taxID = taxID;
+				n2.scores[0][0] = n2.scores[0][1] = n2.scores[1][0] = n2.scores[1][1] = 0;
+				n2.lens[0][0] = n2.lens[0][1] = n2.lens[1][0] = n2.lens[1][1] = 0;
+				n2.scores[rdi][fwi] = sc; n2.lens[rdi][fwi] = (uint32_t)hl;
+				n2.score = 0; n2.hitlen = 0; n2.ts = ts; n2.pid = pid; n2.rank = rank;
+			}
 		}
 	}
-};
+	return nmap;
+}
 
 // rank > 0 with an empty path: the reference's loop `for(; rank < path.size(); ...)` does not
 // run and rank keeps its configured value; handled above because pid < 0 skips the loop.

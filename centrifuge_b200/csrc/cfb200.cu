@@ -819,7 +819,8 @@ struct UnitArgs {
 	IndexView v; Params p; BatchView b;
 	HitRec* hits; uint32_t* nhits; uint32_t cap;
 	uint32_t* nrows;            // per unit
-	const uint64_t* row_off;    // exclusive scan of nrows (n_units+1)
+	uint64_t* row_off;          // per unit: where its rows (ids, hit-map scratch, sparse records) start; handed out by k_prep
+	unsigned long long* row_total;   // allocation counter = total rows of the batch
 	uint64_t* rows; uint32_t* ids; uint64_t rows_cap;
 	Entry* entries; TaxCnt* tcs; OutRec* recs_sparse; uint32_t* nout;
 	unsigned int* overflow;
@@ -842,40 +843,45 @@ __device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, Unit
 	return u.n_mates > 0;
 }
 
-template <int MINB>
+// thread per unit: post-process + sort the hit lists, count the SA rows to resolve, take a slice of the row buffer
+// (one atomic per warp) and write the rows with the scoring plan in their high bits.  EMIT_ONLY re-does only the last
+// two steps on lists that are already final (after the row buffer had to grow).
+template <int MINB, bool EMIT_ONLY>
 __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
 	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
-	if(unit >= a.b.n_units) return;
+	const bool live = unit < a.b.n_units;
 	UnitHits u; const uint8_t* fw[2];
-	uint32_t rows = 0;
-	if(load_unit(a, unit, u, fw)) {
-		Counters local; Counters* lc = nullptr;
-		if(a.ctr) { memset(&local, 0, sizeof local); lc = &local; }
-		for(int r = 0; r < u.n_mates; r++) post_search(a.v, a.p, fw[r], u.rdlen[r], u.L[r][0], u.n[r][0], u.L[r][1], u.n[r][1], lc);
-		SortAndCount sc(a.p, u);
-		for_each_visit(a.p, u, sc);
-		rows = (uint32_t)(sc.rows > 0xFFFFFFFFull ? 0xFFFFFFFFull : sc.rows);
-		if(lc) {
-			atomicAdd(&a.ctr->units, 1ull);
-			if(local.ext_searches) {
-				atomicAdd(&a.ctr->ext_searches, local.ext_searches); atomicAdd(&a.ctr->partial_searches, local.partial_searches);
-				atomicAdd(&a.ctr->ftab_probes, local.ftab_probes); atomicAdd(&a.ctr->sides_search, local.sides_search); atomicAdd(&a.ctr->lf_steps, local.lf_steps);
+	uint64_t rows = 0; bool have = false;
+	if(live && (have = load_unit(a, unit, u, fw))) {
+		if(EMIT_ONLY) { CountRows cr(a.p, u); for_each_visit(a.p, u, cr); rows = cr.rows; }
+		else {
+			Counters local; Counters* lc = nullptr;
+			if(a.ctr) { memset(&local, 0, sizeof local); lc = &local; }
+			for(int r = 0; r < u.n_mates; r++) post_search(a.v, a.p, fw[r], u.rdlen[r], u.L[r][0], u.n[r][0], u.L[r][1], u.n[r][1], lc);
+			SortAndCount sc(a.p, u);
+			for_each_visit(a.p, u, sc);
+			rows = sc.rows;
+			if(lc) {
+				atomicAdd(&a.ctr->units, 1ull);
+				if(local.ext_searches) {
+					atomicAdd(&a.ctr->ext_searches, local.ext_searches); atomicAdd(&a.ctr->partial_searches, local.partial_searches);
+					atomicAdd(&a.ctr->ftab_probes, local.ftab_probes); atomicAdd(&a.ctr->sides_search, local.sides_search); atomicAdd(&a.ctr->lf_steps, local.lf_steps);
+				}
 			}
 		}
+		if(rows > 0xFFFFFFFFull) rows = 0xFFFFFFFFull;
 	}
-	a.nrows[unit] = rows;
-}
-
-__global__ void __launch_bounds__(128) k_rows(const UnitArgs a) {
-	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
-	if(unit >= a.b.n_units) return;
-	const uint64_t off = a.row_off[unit], n = a.row_off[unit + 1] - off;
-	if(n == 0) return;
-	if(off + n > a.rows_cap) { atomicExch(a.overflow, 2u); return; }
-	UnitHits u; const uint8_t* fw[2];
-	if(!load_unit(a, unit, u, fw)) return;
-	EmitRows er(a.p, u, a.rows + off);
-	for_each_visit(a.p, u, er);
+	const unsigned lane = threadIdx.x & 31;
+	uint64_t incl = rows;
+	for(int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, incl, d); if((int)lane >= d) incl += t; }
+	const uint64_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+	unsigned long long base = 0;
+	if(lane == 31 && warp_total) base = atomicAdd(a.row_total, (unsigned long long)warp_total);
+	base = __shfl_sync(0xffffffffu, base, 31);
+	if(!live) return;
+	const uint64_t off = base + incl - rows;
+	a.nrows[unit] = (uint32_t)rows; a.row_off[unit] = off;
+	if(rows && off + rows <= a.rows_cap) { EmitRows er(a.p, u, a.rows + off); for_each_visit(a.p, u, er); }   // else: the host grows the buffer and re-runs EMIT_ONLY
 }
 
 template <int MINB>
@@ -883,14 +889,13 @@ __global__ void __launch_bounds__(128, MINB) k_score(const UnitArgs a) {
 	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
 	if(unit >= a.b.n_units) return;
 	uint32_t no = 0;
-	const uint64_t off = a.row_off[unit], n = a.row_off[unit + 1] - off;
-	if(n > 0 && off + n <= a.rows_cap) {
-		UnitHits u; const uint8_t* fw[2];
-		if(load_unit(a, unit, u, fw)) {
-			ScoreVisit sv(a.v, a.p, u, a.ids + off, a.entries + off);
-			for_each_visit(a.p, u, sv);
-			no = reduce_and_emit(a.v, a.p, u.n_mates == 2, a.entries + off, sv.nmap, a.tcs + off, a.recs_sparse + off);
-		}
+	const uint64_t off = a.row_off[unit], n = a.nrows[unit];
+	if(n > 0 && *a.row_total <= a.rows_cap) {
+		const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
+		int mates = 0;
+		for(int m = 0; m < a.b.n_mates; m++) if(((fl >> m) & 1) && (m ? a.b.len[1][unit] : a.b.len[0][unit]) != 0) mates++;
+		const uint32_t nmap = score_plan(a.v, a.p, a.rows + off, a.ids + off, n, a.entries + off);
+		no = reduce_and_emit(a.v, a.p, mates == 2, a.entries + off, nmap, a.tcs + off, a.recs_sparse + off);
 	}
 	a.nout[unit] = no;
 }
@@ -951,7 +956,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kSearchThreads) k_resolve(const ResolveArgs a) {
 	const unsigned lane = threadIdx.x & 31, gl = lane & 7, gbase = lane & 24, gmask = 0xFFu << gbase;
 	const uint4* sides4 = reinterpret_cast<const uint4*>(a.v.sides);
-	uint64_t n = *a.total; if(n > a.rows_cap) n = a.rows_cap;
+	uint64_t n = *a.total; if(n > a.rows_cap) return;          // the row buffer was too small: slices have holes, the host re-runs the batch
 	const uint64_t lowmask = ((uint64_t)1 << a.v.off_rate) - 1;
 	uint64_t tnext = 0, tend = 0, idx = 0, row = 0;
 	int mode = R_DONE;
@@ -972,7 +977,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_resolve(const ResolveArgs a)
 				if(base >= n) { mode = R_DONE; return false; }
 				tnext = base; tend = base + a.chunk < n ? base + a.chunk : n;
 			}
-			idx = tnext++; row = a.rows[idx];
+			idx = tnext++; row = a.rows[idx] & kRowMask;
 			if(COUNT) c_rows++;
 			mode = settle(row);
 			if(mode != R_DONE) return true;
@@ -1032,7 +1037,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kSearchThreads, 8) k_resolve_t(const ResolveArgs a) {
 	const uint64_t* blocks = a.v.blocks;
 	const uint64_t zblk = a.v.zoff >> 7; const uint32_t zoffb = (uint32_t)(a.v.zoff & 127);
-	uint64_t n = *a.total; if(n > a.rows_cap) n = a.rows_cap;
+	uint64_t n = *a.total; if(n > a.rows_cap) return;          // the row buffer was too small: slices have holes, the host re-runs the batch
 	const uint64_t lowmask = ((uint64_t)1 << a.v.off_rate) - 1;
 	uint64_t idx = 0, row = 0;
 	int mode = R_NEED;
@@ -1053,7 +1058,7 @@ __global__ void __launch_bounds__(kSearchThreads, 8) k_resolve_t(const ResolveAr
 				unsigned long long t = 0;
 				const bool got = pool_take(pool, want, a.task_ctr, (unsigned long long)n, a.chunk, t);
 				if(want) {
-					if(got) { idx = t; row = a.rows[idx]; if(COUNT) c_rows++; mode = settle(row); }
+					if(got) { idx = t; row = a.rows[idx] & kRowMask; if(COUNT) c_rows++; mode = settle(row); }
 					else mode = R_DONE;
 				}
 				if(__any_sync(0xffffffffu, want && !got)) more = false;
@@ -1108,7 +1113,7 @@ template <bool COUNT, bool IDENT>
 __global__ void __launch_bounds__(kSearchThreads) k_resolve_c(const ResolveArgs a) {
 	const unsigned lane = threadIdx.x & 31, gl = lane & 3, gbase = lane & 28, gmask = 0xFu << gbase;
 	const ulonglong2* r16 = reinterpret_cast<const ulonglong2*>(a.v.rank16);
-	uint64_t n = *a.total; if(n > a.rows_cap) n = a.rows_cap;
+	uint64_t n = *a.total; if(n > a.rows_cap) return;          // the row buffer was too small: slices have holes, the host re-runs the batch
 	const uint64_t lowmask = ((uint64_t)1 << a.v.off_rate) - 1;
 	uint64_t idx = 0, row = 0;
 	int mode = R_NEED;
@@ -1129,7 +1134,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_resolve_c(const ResolveArgs 
 				bool got = pool_take(pool, want && gl == 0, a.task_ctr, (unsigned long long)n, a.chunk, t);
 				t = __shfl_sync(0xffffffffu, t, gbase); got = __shfl_sync(0xffffffffu, (int)got, gbase) != 0;
 				if(want) {
-					if(got) { idx = t; row = IDENT ? idx : a.rows[idx]; if(COUNT && gl == 0) c_rows++; mode = settle(row); }
+					if(got) { idx = t; row = IDENT ? idx : (a.rows[idx] & kRowMask); if(COUNT && gl == 0) c_rows++; mode = settle(row); }
 					else mode = R_DONE;
 				}
 				if(__any_sync(0xffffffffu, want && !got)) more = false;
@@ -1195,10 +1200,10 @@ __global__ void __launch_bounds__(kSearchThreads) k_build_walk8(IndexView v, uin
 // Resolve by table: the sequence id of every SA row was precomputed at index load (k_resolve_c<.,true>), so
 // resolving a row is one 2- or 4-byte gather instead of a ~8-step dependent walk.
 __global__ void __launch_bounds__(256) k_lookup(const ResolveArgs a) {
-	uint64_t n = *a.total; if(n > a.rows_cap) n = a.rows_cap;
+	uint64_t n = *a.total; if(n > a.rows_cap) return;          // the row buffer was too small: slices have holes, the host re-runs the batch
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for(uint64_t k = i; k < n; k += stride) { const uint64_t r = a.rows[k]; a.ids[k] = a.v.rtab32 ? __ldg(a.v.rtab32 + r) : (uint32_t)__ldg(a.v.rtab16 + r); }
+	for(uint64_t k = i; k < n; k += stride) { const uint64_t r = a.rows[k] & kRowMask; a.ids[k] = a.v.rtab32 ? __ldg(a.v.rtab32 + r) : (uint32_t)__ldg(a.v.rtab16 + r); }
 }
 
 // =======================================================================================
@@ -1689,12 +1694,12 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	}
 	CK(s.rows.ensure(s.rows_cap)); CK(s.ids.ensure(s.rows_cap)); CK(s.entries.ensure(s.rows_cap)); CK(s.tcs.ensure(s.rows_cap)); CK(s.sparse.ensure(s.rows_cap));
 	s.dense_cap = s.rows_cap; CK(s.dense.ensure(s.dense_cap));
-	CK(cudaMemsetAsync(s.scal.p, 0, 3 * sizeof(unsigned long long), s.st));   // task counters + overflow flag; [3],[4] are rewritten by the scans
+	CK(cudaMemsetAsync(s.scal.p, 0, 4 * sizeof(unsigned long long), s.st));   // task counters, overflow flag, row allocator; [4] is rewritten by the scan
 	if(time_it) CK(cudaEventRecord(s.ev[0], s.st));
 	Counters* ctr = c->count ? c->d_ctr : nullptr;
 	if(c->count && stage == 0) CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), s.st));
 	UnitArgs ua; ua.v = c->view; ua.p = c->prm; ua.b = s.bv; ua.hits = s.hits.p; ua.nhits = s.nhits.p; ua.cap = s.cap;
-	ua.nrows = s.nrows.p; ua.row_off = s.row_off.p; ua.rows = s.rows.p; ua.ids = s.ids.p; ua.rows_cap = s.rows_cap;
+	ua.nrows = s.nrows.p; ua.row_off = s.row_off.p; ua.row_total = s.scal.p + 3; ua.rows = s.rows.p; ua.ids = s.ids.p; ua.rows_cap = s.rows_cap;
 	ua.entries = s.entries.p; ua.tcs = s.tcs.p; ua.recs_sparse = s.sparse.p; ua.nout = s.nout.p;
 	ua.overflow = (unsigned int*)(s.scal.p + 2); ua.ctr = ctr;
 	if(stage == 0) {
@@ -1722,14 +1727,11 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 		search_kernel(variant, c->count)<<<blocks, kSearchThreads, 0, s.st>>>(sa);
 		c->launches++;
 		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
-		k_prep<7><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;          // <= 72 registers
-
-		k_scan_sums<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nrows.p, n, s.bsum.p);
-		k_scan_top<<<1, 1024, 0, s.st>>>(s.bsum.p, scan_blocks, (uint64_t*)(s.scal.p + 3));
-		k_scan_apply<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nrows.p, n, s.bsum.p, (const uint64_t*)(s.scal.p + 3), s.row_off.p);
-		c->launches += 3;
-	} else if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
-	k_rows<<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
+		k_prep<7, false><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;          // <= 72 registers
+	} else {
+		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
+		k_prep<7, true><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
+	}
 	if(time_it) CK(cudaEventRecord(s.ev[2], s.st));
 	ResolveArgs ra; ra.v = c->view; ra.rows = s.rows.p; ra.ids = s.ids.p; ra.ids16 = nullptr; ra.total = (const uint64_t*)(s.scal.p + 3); ra.rows_cap = s.rows_cap;
 	ra.task_ctr = s.scal.p + 1; ra.chunk = c->resolve_mode >= 2 ? 64 : (c->resolve_mode == 1 ? 128 : 4); ra.ctr = ctr;

@@ -92,11 +92,11 @@ extern "C" long long hl_classify(void* hp, const OParams* op, const uint8_t* bas
 			std::vector<uint64_t> rows(sc.rows + 1); std::vector<uint32_t> ids(sc.rows + 1);
 			EmitRows er(p, u, rows.data()); for_each_visit(p, u, er);
 			if(er.k != sc.rows) return -2;
-			for(uint64_t k = 0; k < sc.rows; k++) { ids[k] = resolve_scalar(v, rows[k], &ctr); ctr.rows_resolved++; }
+			for(uint64_t k = 0; k < sc.rows; k++) { ids[k] = resolve_scalar(v, rows[k] & kRowMask, &ctr); ctr.rows_resolved++; }
 			std::vector<Entry> ent(sc.rows + 1); std::vector<TaxCnt> tc(sc.rows + 1); recs.resize(sc.rows + 1);
-			ScoreVisit sv(v, p, u, ids.data(), ent.data()); for_each_visit(p, u, sv);
-			if(sv.k != sc.rows) return -3;
-			no = reduce_and_emit(v, p, u.n_mates == 2, ent.data(), sv.nmap, tc.data(), recs.data());
+			{ CountRows cr(p, u); for_each_visit(p, u, cr); if(cr.rows != sc.rows) return -3; }     // the re-run path counts sorted lists
+			const uint32_t nmap = score_plan(v, p, rows.data(), ids.data(), sc.rows, ent.data());
+			no = reduce_and_emit(v, p, u.n_mates == 2, ent.data(), nmap, tc.data(), recs.data());
 		}
 		out_n[i] = no;
 		if(total + no > cap) return -1;
