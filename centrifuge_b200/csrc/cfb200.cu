@@ -1727,10 +1727,10 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 		search_kernel(variant, c->count)<<<blocks, kSearchThreads, 0, s.st>>>(sa);
 		c->launches++;
 		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
-		k_prep<7, false><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;          // <= 72 registers
+		k_prep<8, false><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;          // <= 64 registers (measured best of 72 / 64 / 40)
 	} else {
 		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
-		k_prep<7, true><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
+		k_prep<8, true><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;
 	}
 	if(time_it) CK(cudaEventRecord(s.ev[2], s.st));
 	ResolveArgs ra; ra.v = c->view; ra.rows = s.rows.p; ra.ids = s.ids.p; ra.ids16 = nullptr; ra.total = (const uint64_t*)(s.scal.p + 3); ra.rows_cap = s.rows_cap;
