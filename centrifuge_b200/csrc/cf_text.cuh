@@ -140,7 +140,7 @@ __device__ __forceinline__ uint32_t warp_add(uint32_t x) { for(int d = 16; d > 0
 __device__ __forceinline__ bool is_space(uint32_t c) { return c == ' ' || (c >= 9 && c <= 13); }
 
 // warp per unit: bases, N filter, seeds, read id length
-__global__ void __launch_bounds__(128) k_tok_bases(const TextArgs a) {
+__global__ void __launch_bounds__(128, 16) k_tok_bases(const TextArgs a) {      // latency-bound: all 64 warp slots of an SM
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t u = blockIdx.x * 4 + (threadIdx.x >> 5);
 	if(u >= a.n_rec) return;
@@ -358,8 +358,8 @@ __global__ void __launch_bounds__(128) k_fmt_plan(const FmtArgs a) {
 	}
 }
 
-static const int kFmtShBytes = 40 * 1024;
-__global__ void __launch_bounds__(128) k_fmt_write(const FmtArgs a) {
+static const int kFmtShBytes = 16 * 1024;      // 128 units x ~60-byte rows fit with room to spare; 12 CTAs per SM stay resident
+__global__ void __launch_bounds__(128, 12) k_fmt_write(const FmtArgs a) {
 	__shared__ char sh[kFmtShBytes];
 	const uint32_t u0 = blockIdx.x * 128, u1 = min(u0 + 128u, a.n_units);
 	const uint64_t base = a.txt_off[u0], end = a.txt_off[u1], span = end - base;

@@ -1536,6 +1536,7 @@ struct cfb_ctx {
 	int search_blocks = 0, resolve_blocks = 0, group = 1; int resolve_mode = 2;   // 0 = 8-lane sides, 1 = thread/blocks, 2 = 4-lane rank16
 	cfb_dbatch resident; bool resident_used = false;
 	double rec_ratio = 2.0;       // records per unit seen so far (sizes the speculative D2H)
+	uint64_t rows_cap0 = 0;       // CFB_ROWS_CAP: initial row-buffer capacity (tests force the grow-and-re-run path with it)
 	TextCtx* text = nullptr;
 };
 
@@ -1627,6 +1628,7 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 	else if(c->resolve_mode == 1) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_t<false>, kSearchThreads, 0));
 	else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
 	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
+	{ const char* rc0 = getenv("CFB_ROWS_CAP"); if(rc0) c->rows_cap0 = strtoull(rc0, NULL, 10); }
 	const char* cnt = getenv("CFB_COUNT");
 	c->count = cnt && cnt[0] == '1';
 	#undef CKC
@@ -1690,7 +1692,7 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 		const uint32_t W = (s.maxlen + 31) / 32 + 1;
 		CK(s.pk.ensure(ntasks * W + 2)); CK(s.nm.ensure(ntasks * W + 2)); CK(s.nrows.ensure(n)); CK(s.row_off.ensure(n + 1));
 		CK(s.bsum.ensure(scan_blocks + 1)); CK(s.nout.ensure(n)); CK(s.out_off.ensure(n + 1)); CK(s.rec_off32.ensure(n + 1));
-		s.rows_cap = std::max<uint64_t>(s.rows_cap, std::max<uint64_t>(n * 12, 4096));
+		s.rows_cap = std::max<uint64_t>(s.rows_cap, c->rows_cap0 ? c->rows_cap0 : std::max<uint64_t>(n * 12, 4096));
 	}
 	CK(s.rows.ensure(s.rows_cap)); CK(s.ids.ensure(s.rows_cap)); CK(s.entries.ensure(s.rows_cap)); CK(s.tcs.ensure(s.rows_cap)); CK(s.sparse.ensure(s.rows_cap));
 	s.dense_cap = s.rows_cap; CK(s.dense.ensure(s.dense_cap));

@@ -94,6 +94,7 @@ LAYOUT_VARIANTS = {
     "ftabk11": {"CFB_FTABK": "11"},
     "ftabk12_walk_resolve": {"CFB_FTABK": "12", "CFB_RESOLVE_TABLE": "0"},
     "coop8": {"CFB_GROUP": "8", "CFB_LEGACY_LAYOUTS": "1"},
+    "tiny_row_buffer": {"CFB_ROWS_CAP": "64"},          # every batch overflows the row buffer once and re-runs from the row stage
 }
 
 
