@@ -88,6 +88,9 @@ def test_fastq_se_mixed_lengths_all_on_device(syn, tmp_path):
         got, st = run_ours(args, tmp_path, "our", block=100000)
         assert got == want, extra
         assert st["fallbacks"] == 0 and st["host"] == 0 and st["text"] == len(reads) and st["spans"] > 5, st
+    # row-buffer overflow inside a span: classification stages re-run, the formatter follows
+    got, st = run_ours(["-q", "-x", base, "-U", fq], tmp_path, "rows", block=100000, extra_env={"CFB_ROWS_CAP": "64"})
+    assert got == run_ref(["-q", "-x", base, "-U", fq], tmp_path, "ref") and st["fallbacks"] == 0
     # one big span and the forced host reader give the same bytes
     got, st = run_ours(["-q", "-x", base, "-U", fq], tmp_path, "big")
     assert got == run_ref(["-q", "-x", base, "-U", fq], tmp_path, "ref") and st["spans"] == 1
