@@ -11,6 +11,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
 
 
+def pytest_sessionstart(session):
+    """The suite exercises the built library and CLI: build them when missing or stale (nvcc cross-compiles
+    without a GPU; a no-op when everything is current)."""
+    from centrifuge_b200 import build as b
+    b.build(verbose=False)
+
+
 @pytest.fixture(scope="session")
 def adv_base():
     import util
