@@ -30,6 +30,18 @@ def test_kreport_from_tsv_matches_reference_script(case, suffix, args, tmp_path)
         assert f.read() == g.read()
 
 
+@pytest.mark.parametrize("suffix,args", [("", (0, 0, 0, 0, 0)), (".zeros", (1, 0, 0, 0, 0)), (".minscore", (0, 1, 300, 0, 0)), (".minlen", (0, 0, 0, 1, 40))])
+def test_kreport_corner_cases_match_reference_script(suffix, args, tmp_path):
+    """LCA merging of equal consecutive readIDs, dotted / unknown taxIDs to the root, filtered rows between rows of one read."""
+    base = util.golden_index("adv")
+    out = str(tmp_path / "k.txt")
+    rc = lib().cfb_kreport(base.encode(), os.path.join(util.GOLDEN, "kreport_quirks.tsv").encode(), out.encode(), C.c_int(args[0]), C.c_int(args[1]),
+                           C.c_longlong(args[2]), C.c_int(args[3]), C.c_longlong(args[4]))
+    assert rc == 0
+    with open(out, "rb") as f, open(os.path.join(util.GOLDEN, "kreport_quirks%s.kreport.txt" % suffix), "rb") as g:
+        assert f.read() == g.read()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("reader", ["text", "host"])
 @pytest.mark.parametrize("case,opts", [("default", []), ("k1", ["-k", "1"]), ("host", ["--host-taxids", "100,1005", "-k", "2"])])
