@@ -556,6 +556,7 @@ __global__ void k_build_ftab2(IndexView v, uint64_t n, uint64_t* ftab2) {
 	if(fi >= n) return;
 	ftab2[fi * 2] = ftab_hi(v, v.ftab[fi]); ftab2[fi * 2 + 1] = ftab_lo(v, v.ftab[fi + 1]);
 }
+static const uint32_t kListNoLong = 0x80000000u;             // flag in nhits[]: the strand has no hit of min_hitlen bases
 static const uint64_t kOccMask = 0x7fffffffffffffffull;
 static const uint64_t kWalkRowMask = (1ull << 40) - 1ull;   // walk8 entry: row in the low 40 bits
 static const int kJumpRows = 1;                             // widest range advanced through walk8.  Ranges of 2-4 adjacent rows can take the same
@@ -654,6 +655,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 	ReadRegs<RW> rd;
 	uint64_t top = 0, bot = 0, fi = 0;
 	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0, slow_until = 0;
+	bool nolong = true;      // no hit of this strand reaches min_hitlen (kListNoLong tells the per-unit kernels)
 	int mode = M_NEED;
 	unsigned long long c_ps = 0, c_ft = 0, c_sides = 0, c_lf = 0;
 	WarpPool pool; pool.base = pool.end = 0;
@@ -663,12 +665,13 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 		if(nh < a.cap) { HitRec* h = a.hits + (size_t)tid * a.cap + nh; h->top = t; h->bot = b; h->bwoff = off; h->len = len; }
 		else atomicExch(a.overflow, 1u);
 		nh++;
+		if(len >= a.p.min_hitlen) nolong = false;
 	};
 	// searchForwardAndReverse restart policy (classifier.h:686-766): true = another partial search starts at cur
 	auto after_hit = [&](uint32_t hlen) -> bool {
 		bool done = cur >= rlen;
 		if(!done) { if(hlen > a.p.increment) cur += 1; if(cur + a.p.min_hitlen >= rlen) done = true; }
-		if(done) { a.nhits[tid] = nh; mode = M_NEED; return false; }
+		if(done) { a.nhits[tid] = nh | (nolong ? kListNoLong : 0u); mode = M_NEED; return false; }
 		return true;
 	};
 	// partialSearch prologue (hi_aligner.h:939-982) at `cur`: ends in M_FTAB (fi set) or M_NEED
@@ -676,7 +679,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 		for(;;) {
 			if(COUNT) c_ps++;
 			offset = cur;
-			if(rlen - cur < fc) { emit(kOff, kOff, offset, rlen - offset); a.nhits[tid] = nh; mode = M_NEED; return; }
+			if(rlen - cur < fc) { emit(kOff, kOff, offset, rlen - offset); a.nhits[tid] = nh | (nolong ? kListNoLong : 0u); mode = M_NEED; return; }
 			uint64_t win; uint32_t nwin; rd.window(cur, win, nwin);
 			const uint32_t nbits = nwin & ((1u << fc) - 1u);
 			if(nbits) {
@@ -714,7 +717,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 						const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
 						nh = 0; rlen = a.b.len[mate][unit];
 						if(!((fl >> mate) & 1) || rlen == 0) a.nhits[tid] = 0;          // filtered mate: stays M_NEED
-						else { rd.load(a.pk + (size_t)tid * a.W, a.nm + (size_t)tid * a.W, a.W); cur = 0; slow_until = 0; start_search(); }
+						else { rd.load(a.pk + (size_t)tid * a.W, a.nm + (size_t)tid * a.W, a.W); cur = 0; slow_until = 0; nolong = true; start_search(); }
 					} else mode = M_DONE;
 				}
 				if(__any_sync(0xffffffffu, want && !got)) more = false;      // global counter ran past the end
@@ -836,8 +839,13 @@ __device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, Unit
 		if(len == 0) continue;
 		const int r = u.n_mates++;
 		const size_t t0 = ((size_t)unit * a.b.n_mates + m) * 2;
-		u.L[r][0] = a.hits + t0 * a.cap;       u.n[r][0] = min(a.nhits[t0], a.cap);
-		u.L[r][1] = a.hits + (t0 + 1) * a.cap; u.n[r][1] = min(a.nhits[t0 + 1], a.cap);
+		const uint32_t raw0 = a.nhits[t0], raw1 = a.nhits[t0 + 1];
+		u.L[r][0] = a.hits + t0 * a.cap;       u.n[r][0] = min(raw0 & ~kListNoLong, a.cap);
+		u.L[r][1] = a.hits + (t0 + 1) * a.cap; u.n[r][1] = min(raw1 & ~kListNoLong, a.cap);
+		// A strand list without a hit of min_hitlen bases matters only to the extension step, which needs such a hit on
+		// BOTH strands (classifier.h:790-802); everything later (trimming within a list, strand choice, counting,
+		// scoring) ignores or only shortens short hits.  So unless both strands have one, such a list is never read.
+		if((raw0 | raw1) & kListNoLong) { if(raw0 & kListNoLong) u.n[r][0] = 0; if(raw1 & kListNoLong) u.n[r][1] = 0; }
 		u.rdlen[r] = len; fw[r] = a.b.bases + a.b.off[m][unit];
 	}
 	return u.n_mates > 0;
