@@ -645,7 +645,7 @@ template <int RW> struct ReadRegs {
 };
 
 template <bool COUNT, int RW>
-__global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a) {
+__global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a) {      // 9 CTAs per SM at 52 registers; forcing 10 (48 registers) measured no faster: the DRAM gather rate is the limit
 	const ulonglong2* r16 = reinterpret_cast<const ulonglong2*>(a.v.rank16);
 	const ulonglong2* ftab2 = reinterpret_cast<const ulonglong2*>(a.v.ftab2);
 	const ulonglong2* ftabk = reinterpret_cast<const ulonglong2*>(a.v.ftabk);
