@@ -902,11 +902,20 @@ bool read_fastq(FileBuf& fb, RawRead& r, u64 readCnt, bool& first) {
 	}
 	while(true) { int d = fb.get(); if(d < 0 || d == '\n' || d == '\r') { while(fb.peek() == '\n' || fb.peek() == '\r') fb.get(); break; } }
 	if(r.seq.empty()) { if(fb.peek() == '@') fb.get(); return true; }
-	while(true) {
+	while(true) {                                          // pat.cpp:1042-1078, phred33 (qual.h:136-142)
 		c = fb.get();
+		if(c == ' ') {
+			fprintf(stderr, "Error: Encountered one or more spaces while parsing the quality string for read %s.  If this is a FASTQ file with integer (non-ASCII-encoded) qualities, try re-running with the --integer-quals option.\n", r.name.c_str());
+			exit(1);
+		}
 		if(c < 0) break;
-		if(c != '\r' && c != '\n') r.qual.push_back((char)c); else break;
+		if(c != '\r' && c != '\n') {
+			if((int)(signed char)c < 33) { fprintf(stderr, "Saw ASCII character %d but expected 33-based Phred qual.\n", (int)(signed char)c); exit(1); }
+			r.qual.push_back((char)c);
+		} else break;
 	}
+	if(r.qual.size() < r.seq.size()) { fprintf(stderr, "Error: Read %s has more read characters than quality values.\n", r.name.c_str()); exit(1); }
+	if(r.qual.size() > r.seq.size() + 1) { fprintf(stderr, "Error: Read %s has more quality values than read characters.\n", r.name.c_str()); exit(1); }
 	if(r.qual.size() > r.seq.size()) r.qual.resize(r.seq.size());
 	while(fb.peek() == '\n' || fb.peek() == '\r') fb.get();
 	c = fb.get();                                          // '@' of the next record or EOF

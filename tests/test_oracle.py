@@ -210,3 +210,28 @@ def test_product_loader_host_only(adv_base):
     with pytest.raises(capi.CfbError):
         capi.Context(ix)
     ix.close()
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref reference binaries not shipped")
+@pytest.mark.parametrize("kind", ["too_many", "too_few", "space", "control", "plus_one"])
+def test_oracle_reader_rejects_what_the_reference_rejects(kind, tmp_path):
+    """FASTQ quality-string rules (pat.cpp:1042-1078): same message and a failing exit status, or the same output."""
+    base = util.build_index("syn_a", 5, 4, 60000, seed=7, strains=True)
+    seqs = util.synth.make_genomes(5, 4, 60000, 7)
+    reads = util.synth.sample_reads(seqs, 300, 80, seed=9)
+    fq = str(tmp_path / "q.fq")
+    with open(fq, "wb") as f:
+        for i, (name, a) in enumerate(reads):
+            q = b"F" * len(a)
+            if i == 200:
+                q = {"too_many": q + b"FF", "too_few": q[:-1], "space": q[:10] + b" " + q[11:], "control": q[:10] + b"\x1f" + q[11:], "plus_one": q + b"F"}[kind]
+            f.write(b"@" + name.encode() + b"\n" + a.tobytes() + b"\n+\n" + q + b"\n")
+    outs = []
+    for exe in (util.REF_CLASS, util.ORACLE_BIN):
+        p = subprocess.run([exe, "-q", "-x", base, "-U", fq, "-S", str(tmp_path / "o.tsv"), "--report-file", str(tmp_path / "o.rep")],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        msgs = [l for l in p.stderr.decode().splitlines() if l.startswith("Error") or l.startswith("Saw ASCII")]
+        with open(tmp_path / "o.tsv", "rb") as f:
+            outs.append((p.returncode != 0, msgs, f.read() if p.returncode == 0 else b""))
+    assert outs[0] == outs[1]
+    assert outs[0][0] == (kind != "plus_one")
