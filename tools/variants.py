@@ -15,9 +15,6 @@ batch = capi.make_batch(codes.reshape(-1), offs, lens, None, None, flags)
 ix = capi.Index(base, 0)
 ref = None
 for g in sys.argv[1:]:
-    if ":" in g:
-        g, mb = g.split(":"); os.environ["CFB_MINB"] = mb
-        # the kernel choice is cached per process for MINB: only the first value counts
     os.environ["CFB_GROUP"] = g
     ctx = capi.Context(ix)
     db = ctx.upload(batch)
