@@ -280,6 +280,28 @@ static void em_step(const EmFlat& f, const std::vector<double>& p, std::vector<d
 	for(size_t i = 0; i < pn.size(); i++) pn[i] = pn[i] / f.len[i] / sum;
 }
 
+// SQUAREM-accelerated iteration on the host (aln_sink.h:410-480): same loop the device version restates
+static void em_iterate(const EmFlat& f, std::vector<double>& p, size_t& it, double& diff) {
+	std::vector<double> pn(p.size()), pn2(p.size()), pr(p.size()), pv(p.size());
+	it = 0; diff = 0.0;
+	for(;;) {
+		em_step(f, p, pn);
+		em_step(f, pn, pn2);
+		double ssr = 0.0, ssv = 0.0;
+		for(size_t i = 0; i < p.size(); i++) { pr[i] = pn[i] - p[i]; ssr += pr[i] * pr[i]; pv[i] = pn2[i] - pn[i] - pr[i]; ssv += pv[i] * pv[i]; }
+		if(ssv > 0.0) {
+			const double g = -sqrt(ssr / ssv);
+			for(size_t i = 0; i < p.size(); i++) pn2[i] = std::max(0.0, p[i] - 2 * g * pr[i] + g * g * pv[i]);
+			em_step(f, pn2, pn);
+		}
+		diff = 0.0;
+		for(size_t i = 0; i < p.size(); i++) diff += (p[i] > pn[i] ? p[i] - pn[i] : pn[i] - p[i]);
+		if(diff < 0.0000000001) break;
+		if(++it >= 10000) break;
+		p = pn;
+	}
+}
+
 extern "C" int cfb_em_abundance(int device, uint64_t n, uint64_t K, const uint64_t* count, const uint64_t* key_off, const uint32_t* target,
                                 const uint64_t* len, double* p, uint64_t* iters, double* last_diff);
 extern "C" const char* cfb_em_last_error(void);
@@ -342,25 +364,7 @@ static void calc_abundance(const HostIndex& h, Species& sp, size_t& iters, doubl
 			std::cerr << "Error: " << cfb_em_last_error() << std::endl; throw 1;
 		}
 		it = (size_t)iters64;
-	} else {
-		std::vector<double> pn(p.size()), pn2(p.size()), pr(p.size()), pv(p.size());
-		for(;;) {
-			em_step(f, p, pn);
-			em_step(f, pn, pn2);
-			double ssr = 0.0, ssv = 0.0;
-			for(size_t i = 0; i < p.size(); i++) { pr[i] = pn[i] - p[i]; ssr += pr[i] * pr[i]; pv[i] = pn2[i] - pn[i] - pr[i]; ssv += pv[i] * pv[i]; }
-			if(ssv > 0.0) {
-				const double g = -sqrt(ssr / ssv);
-				for(size_t i = 0; i < p.size(); i++) pn2[i] = std::max(0.0, p[i] - 2 * g * pr[i] + g * g * pv[i]);
-				em_step(f, pn2, pn);
-			}
-			diff = 0.0;
-			for(size_t i = 0; i < p.size(); i++) diff += (p[i] > pn[i] ? p[i] - pn[i] : pn[i] - p[i]);
-			if(diff < 0.0000000001) break;
-			if(++it >= 10000) break;
-			p = pn;
-		}
-	}
+	} else em_iterate(f, p, it, diff);
 	iters = it; last_diff = diff;
 	sp.abundance_len.clear();
 	for(std::map<uint64_t, uint64_t>::iterator i = t2n.begin(); i != t2n.end(); ++i) sp.abundance_len[i->first] = p[i->second];
@@ -904,6 +908,20 @@ static int parse_args(int argc, const char** argv, Options& o, bool& exit_now) {
 }
 
 }  // namespace
+
+// The host iteration on caller-provided flattened tables (what cfb_run uses for small tables); same contract as
+// cfb_em_abundance, no device involved.
+extern "C" int cfb_em_abundance_host(uint64_t n, uint64_t K, const uint64_t* count, const uint64_t* key_off, const uint32_t* target,
+                                     const uint64_t* len, double* p, uint64_t* iters, double* last_diff) {
+	if(!count || !key_off || !target || !len || !p || !iters || !last_diff || n == 0) return CFB_EINVAL;
+	EmFlat f; f.count.assign(count, count + K); f.key_off.assign(key_off, key_off + K + 1); f.target.assign(target, target + key_off[K]); f.len.assign(len, len + n);
+	for(uint64_t t = 0; t < key_off[K]; t++) if(target[t] >= n) return CFB_EINVAL;
+	std::vector<double> pv(p, p + n); size_t it = 0; double diff = 0.0;
+	em_iterate(f, pv, it, diff);
+	std::copy(pv.begin(), pv.end(), p);
+	*iters = it; *last_diff = diff;
+	return CFB_OK;
+}
 
 // Stand-alone form of the same report: classification TSV file in, Kraken-style report out (host only).
 extern "C" int cfb_kreport(const char* index_base, const char* tsv_path, const char* out_path, int show_zeros,

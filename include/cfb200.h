@@ -236,6 +236,9 @@ int cfb_run(int argc, const char** argv);
 int cfb_em_abundance(int device, uint64_t n, uint64_t K, const uint64_t* count, const uint64_t* key_off, const uint32_t* target,
                      const uint64_t* len, double* p, uint64_t* iters, double* last_diff);
 const char* cfb_em_last_error(void);
+/* The same iteration on the host (what cfb_run uses for small tables). */
+int cfb_em_abundance_host(uint64_t n, uint64_t K, const uint64_t* count, const uint64_t* key_off, const uint32_t* target,
+                          const uint64_t* len, double* p, uint64_t* iters, double* last_diff);
 
 /* Kraken-style report.  Replaces the `centrifuge-kreport` script (centrifuge-kreport:60-260,
  * default LCA mode; its --show-zeros / --min-score / --min-length options): same bytes from the same classification
