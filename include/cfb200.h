@@ -84,8 +84,9 @@ typedef struct {
 } cfb_params;
 void cfb_params_default(cfb_params*);
 
-/* One context = one CUDA stream set + staging buffers, bound to the index's device.
- * max_units / max_bases size the device buffers (they grow on demand). */
+/* One context = cfb_ctx_slots() CUDA streams with their device and pinned staging buffers, bound to the index's
+ * device.  Buffers are sized by the batches that arrive and grow on demand (about 3.5 KB of HBM per read of a batch in
+ * flight).  A context is not thread-safe; create one per host thread that submits work. */
 int  cfb_ctx_create(const cfb_index*, const cfb_params*, cfb_ctx** out);
 void cfb_ctx_destroy(cfb_ctx*);
 
@@ -126,8 +127,10 @@ typedef struct {
 /* Synchronous: H2D, kernels, D2H, returns when the result is in host memory. */
 int cfb_classify_batch(cfb_ctx*, const cfb_batch*, cfb_result* out);
 
-/* Pipelined: up to cfb_ctx_slots() batches in flight on independent streams.
- * submit copies the caller's arrays into pinned staging before returning. */
+/* Pipelined: up to cfb_ctx_slots() batches in flight on independent streams.  Arrays that live in pinned memory
+ * (cfb_host_alloc) are DMA'd from where they are and must stay untouched until the matching wait; pageable arrays are
+ * copied into pinned staging before submit returns.  The records follow the kernels home without a size round trip,
+ * so a wait is normally a single stream synchronisation. */
 int cfb_ctx_slots(const cfb_ctx*);
 int cfb_classify_submit(cfb_ctx*, int slot, const cfb_batch*);
 int cfb_classify_wait(cfb_ctx*, int slot, cfb_result* out);
