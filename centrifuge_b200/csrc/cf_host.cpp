@@ -108,9 +108,14 @@ static bool parse_fasta(FileIn& in, Rec& r, uint64_t& count, bool& first, int tr
 	int c = in.get();
 	if(c < 0) return false;
 	while(c == '#' || c == ';' || c == '\r' || c == '\n') {
-		if(c == '#' || c == ';') { for(;;) { int d = in.peek(); if(d < 0 || d == '\n' || d == '\r') break; in.get(); } }
+		// FileBuf::peekUptoNewline (filebuf.h:306-318): drop the rest of the line the cursor is in, then every line end.
+		// For a comment that is the comment line; after a *line end* (only possible before the first record) it is
+		// the whole next line -- a leading blank line makes the reference swallow the first header (pat.cpp:744-748).
+		for(;;) { int d = in.peek(); if(d < 0 || d == '\n' || d == '\r') break; in.get(); }
+		while(in.peek() == '\n' || in.peek() == '\r') in.get();
 		c = in.get();
-		if(c < 0) return false;
+		if(c < 0 && !first) return false;
+		if(c < 0) break;
 	}
 	if(first) { if(c != '>') { std::cerr << "Error: reads file does not look like a FASTA file" << std::endl; throw 1; } first = false; }
 	c = in.get();
@@ -908,6 +913,30 @@ static int parse_args(int argc, const char** argv, Options& o, bool& exit_now) {
 }
 
 }  // namespace
+
+// Test hook (host only): run the record-level reader over a file and dump, per read, name / bases / seed / filter
+// verdict, so that tests can diff it with the oracle's reader without a GPU.
+extern "C" int cfb_test_parse(const char* path, int fasta, int trim5, int trim3, uint32_t seed, const char* out_path) {
+	if(!path || !out_path) return CFB_EINVAL;
+	init_tables();
+	FileIn in;
+	if(!in.open(path)) return CFB_EIO;
+	FILE* fo = fopen(out_path, "wb");
+	if(!fo) { in.close(); return CFB_EIO; }
+	int rc = CFB_OK;
+	try {
+		Rec r; uint64_t cnt = 0; bool first = true;
+		for(;;) {
+			const bool ok = fasta ? parse_fasta(in, r, cnt, first, trim5, trim3) : parse_fastq(in, r, cnt, first, trim5, trim3);
+			if(!ok) break;
+			fputs(r.name.c_str(), fo); fputc('\t', fo);
+			for(size_t i = 0; i < r.seq.size(); i++) fputc("ACGTN"[r.seq[i]], fo);
+			fprintf(fo, "\t%u\t%d\n", read_seed(r, seed), passes_filters(r.seq) ? 1 : 0);
+		}
+	} catch(int) { rc = 1; }
+	fclose(fo); in.close();
+	return rc;
+}
 
 // The host iteration on caller-provided flattened tables (what cfb_run uses for small tables); same contract as
 // cfb_em_abundance, no device involved.

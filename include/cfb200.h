@@ -194,6 +194,9 @@ void  cfb_host_free(void*);
  * arrays of rows.  out[i] = LF(rows[i], chars[i]) ; chars[i] > 3 means BWT[rows[i]]. */
 int cfb_test_lf(const cfb_index*, const uint64_t* rows, const uint8_t* chars, uint64_t n, uint64_t* out);
 int cfb_test_resolve(const cfb_index*, const uint64_t* rows, uint64_t n, uint32_t* out);
+/* Host-only test hook: the record-level FASTA/FASTQ reader of cfb_run over a file; one line per read
+ * "name<TAB>bases<TAB>seed<TAB>passes filters".  Returns 1 where the reference would stop with an error. */
+int cfb_test_parse(const char* path, int fasta, int trim5, int trim3, uint32_t seed, const char* out_path);
 
 const char* cfb_last_error(void);
 const char* cfb_version(void);

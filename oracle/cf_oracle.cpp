@@ -842,10 +842,14 @@ bool read_fasta(FileBuf& fb, RawRead& r, u64 readCnt, bool& first, bool& empty) 
 	int c = fb.get();
 	if(c < 0) return false;
 	while(c == '#' || c == ';' || c == '\r' || c == '\n') {
-		// peekUptoNewline: skip to end of line
-		if(c == '#' || c == ';') { while(true) { int d = fb.peek(); if(d < 0 || d == '\n' || d == '\r') break; fb.get(); } }
+		// FileBuf::peekUptoNewline (filebuf.h:306-318): drop the rest of the line the cursor is in, then every line end.
+		// For a comment that is the comment line; after a *line end* (only possible before the first record) it is
+		// the whole next line -- a leading blank line makes the reference swallow the first header (pat.cpp:744-748).
+		while(true) { int d = fb.peek(); if(d < 0 || d == '\n' || d == '\r') break; fb.get(); }
+		while(fb.peek() == '\n' || fb.peek() == '\r') fb.get();
 		c = fb.get();
-		if(c < 0) return false;
+		if(c < 0 && !first) return false;
+		if(c < 0) break;
 	}
 	if(first) { if(c != '>') { fprintf(stderr, "Error: reads file does not look like a FASTA file\n"); exit(1); } first = false; }
 	c = fb.get();
@@ -1088,7 +1092,7 @@ std::vector<u64> parse_ids(const char* s) {
 }  // namespace
 
 extern "C" int cfo_main(int argc, const char** argv) {
-	std::string idx, u, m1, m2, out = "-", report = "centrifuge_report.tsv", statsf;
+	std::string idx, u, m1, m2, out = "-", report = "centrifuge_report.tsv", statsf, dumpf;
 	bool fasta = false, abundance = true;
 	cfo_params p; memset(&p, 0, sizeof p); p.khits = 5; p.min_hitlen = 22; p.tree_traverse = 1; p.class_rank_slot = 0;
 	std::vector<u64> host, excl;
@@ -1103,6 +1107,7 @@ extern "C" int cfo_main(int argc, const char** argv) {
 		else if(a == "--classification-rank") { uint8_t r = rank_to_pathID(rank_id(NEXT)); p.class_rank_slot = r; }
 		else if(a == "--no-abundance") abundance = false; else if(a == "-p") (void)NEXT;
 		else if(a == "--stats") statsf = NEXT;
+		else if(a == "--dump-reads") dumpf = NEXT;      // reader only: name, bases, seed, filter verdict per read (tests diff it with the product's reader)
 		else { fprintf(stderr, "cf_oracle: unknown option %s\n", a.c_str()); return 1; }
 		#undef NEXT
 	}
@@ -1131,6 +1136,11 @@ extern "C" int cfo_main(int argc, const char** argv) {
 		u32 seedA = gen_rand_seed(ra, 0), seedB = paired ? gen_rand_seed(rb, 0) : 0;
 		bool pair = paired && !rb.seq.empty();
 		bool f1 = n_filter(ra.seq) && ra.seq.size() >= 2, f2 = pair ? (n_filter(rb.seq) && rb.seq.size() >= 2) : false;
+		if(!dumpf.empty()) {
+			static FILE* df = NULL; if(!df) df = fopen(dumpf.c_str(), "wb");
+			if(df) { fputs(ra.name.c_str(), df); fputc('\t', df); for(size_t q = 0; q < ra.seq.size(); q++) fputc("ACGTN"[ra.seq[q]], df); fprintf(df, "\t%u\t%d\n", seedA, f1 ? 1 : 0); fflush(df); }
+			continue;
+		}
 		Rng rnd; rnd.init((f1 && f2) ? (seedA ^ seedB) : seedA);   // centrifuge.cpp:2609-2613
 		recs.clear();
 		int64_t max_score = 0;
