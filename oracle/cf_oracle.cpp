@@ -836,7 +836,7 @@ struct FileBuf {
 };
 
 // returns false at EOF
-bool read_fasta(FileBuf& fb, RawRead& r, u64 readCnt, bool& first, bool& empty) {
+bool read_fasta(FileBuf& fb, RawRead& r, u64 readCnt, bool& first, bool& empty, int trim5 = 0, int trim3 = 0) {
 	const uint8_t* a2d = asc2dna_tab();
 	r.name.clear(); r.seq.clear(); r.qual.clear(); empty = false;
 	int c = fb.get();
@@ -869,16 +869,18 @@ bool read_fasta(FileBuf& fb, RawRead& r, u64 readCnt, bool& first, bool& empty) 
 	}
 	if(c == '>') { empty = true; return true; }            // never true here in practice (c is not advanced onto '>')
 	if(fb.peek() == '>' && (c == '\n' || c == '\r')) { empty = true; return true; }
+	int begin = 0;
 	while(c != '>' && c >= 0) {
-		if(dnacat(c)) { r.seq.push_back(a2d[c]); r.qual.push_back('I'); }
+		if(dnacat(c) && begin++ >= trim5) { r.seq.push_back(a2d[c]); r.qual.push_back('I'); }   // pat.cpp:826-830
 		if(fb.peek() == '>') break;
 		c = fb.get();
 	}
+	if(trim3 > 0) { const size_t keep = r.seq.size() > (size_t)trim3 ? r.seq.size() - trim3 : 0; r.seq.resize(keep); r.qual.resize(keep); }   // trimEnd :833-834
 	if(r.name.empty()) { char b[32]; snprintf(b, sizeof b, "%llu", (unsigned long long)readCnt); r.name = b; }
 	return true;
 }
 
-bool read_fastq(FileBuf& fb, RawRead& r, u64 readCnt, bool& first) {
+bool read_fastq(FileBuf& fb, RawRead& r, u64 readCnt, bool& first, int trim5 = 0, int trim3 = 0) {
 	const uint8_t* a2d = asc2dna_tab();
 	r.name.clear(); r.seq.clear(); r.qual.clear();
 	int c;
@@ -898,14 +900,17 @@ bool read_fastq(FileBuf& fb, RawRead& r, u64 readCnt, bool& first) {
 		}
 		r.name.push_back((char)c);
 	}
+	int nread = 0;
 	while(c != '+') {
 		if(c == '.') c = 'N';
-		if(isalpha(c)) r.seq.push_back(a2d[c]);
+		if(isalpha(c)) { if(nread >= trim5) r.seq.push_back(a2d[c]); nread++; }      // pat.cpp:939-946
 		c = fb.get();
 		if(c < 0) return false;
 	}
+	if(trim3 > 0) r.seq.resize(r.seq.size() > (size_t)trim3 ? r.seq.size() - trim3 : 0);   // :970-982
 	while(true) { int d = fb.get(); if(d < 0 || d == '\n' || d == '\r') { while(fb.peek() == '\n' || fb.peek() == '\r') fb.get(); break; } }
-	if(r.seq.empty()) { if(fb.peek() == '@') fb.get(); return true; }
+	if(nread == 0) { if(fb.peek() == '@') fb.get(); return true; }
+	int qi = 0;
 	while(true) {                                          // pat.cpp:1042-1078, phred33 (qual.h:136-142)
 		c = fb.get();
 		if(c == ' ') {
@@ -914,10 +919,14 @@ bool read_fastq(FileBuf& fb, RawRead& r, u64 readCnt, bool& first) {
 		}
 		if(c < 0) break;
 		if(c != '\r' && c != '\n') {
-			if((int)(signed char)c < 33) { fprintf(stderr, "Saw ASCII character %d but expected 33-based Phred qual.\n", (int)(signed char)c); exit(1); }
-			r.qual.push_back((char)c);
+			if(qi >= trim5) {
+				if((int)(signed char)c < 33) { fprintf(stderr, "Saw ASCII character %d but expected 33-based Phred qual.\n", (int)(signed char)c); exit(1); }
+				r.qual.push_back((char)c);
+			}
+			qi++;
 		} else break;
 	}
+	if(trim3 > 0) r.qual.resize(r.qual.size() > (size_t)trim3 ? r.qual.size() - trim3 : 0);
 	if(r.qual.size() < r.seq.size()) { fprintf(stderr, "Error: Read %s has more read characters than quality values.\n", r.name.c_str()); exit(1); }
 	if(r.qual.size() > r.seq.size() + 1) { fprintf(stderr, "Error: Read %s has more quality values than read characters.\n", r.name.c_str()); exit(1); }
 	if(r.qual.size() > r.seq.size()) r.qual.resize(r.seq.size());
@@ -1093,7 +1102,7 @@ std::vector<u64> parse_ids(const char* s) {
 
 extern "C" int cfo_main(int argc, const char** argv) {
 	std::string idx, u, m1, m2, out = "-", report = "centrifuge_report.tsv", statsf, dumpf;
-	bool fasta = false, abundance = true;
+	bool fasta = false, abundance = true; int trim5 = 0, trim3 = 0;
 	cfo_params p; memset(&p, 0, sizeof p); p.khits = 5; p.min_hitlen = 22; p.tree_traverse = 1; p.class_rank_slot = 0;
 	std::vector<u64> host, excl;
 	for(int i = 1; i < argc; i++) {
@@ -1107,6 +1116,7 @@ extern "C" int cfo_main(int argc, const char** argv) {
 		else if(a == "--classification-rank") { uint8_t r = rank_to_pathID(rank_id(NEXT)); p.class_rank_slot = r; }
 		else if(a == "--no-abundance") abundance = false; else if(a == "-p") (void)NEXT;
 		else if(a == "--stats") statsf = NEXT;
+		else if(a == "-5" || a == "--trim5") trim5 = atoi(NEXT); else if(a == "-3" || a == "--trim3") trim3 = atoi(NEXT);
 		else if(a == "--dump-reads") dumpf = NEXT;      // reader only: name, bases, seed, filter verdict per read (tests diff it with the product's reader)
 		else { fprintf(stderr, "cf_oracle: unknown option %s\n", a.c_str()); return 1; }
 		#undef NEXT
@@ -1129,10 +1139,10 @@ extern "C" int cfo_main(int argc, const char** argv) {
 	RawRead ra, rb; std::vector<cfo_rec> recs; std::string line;
 	while(true) {
 		bool okA, emptyA = false, emptyB = false;
-		okA = fasta ? read_fasta(fa, ra, cntA, firstA, emptyA) : read_fastq(fa, ra, cntA, firstA);
+		okA = fasta ? read_fasta(fa, ra, cntA, firstA, emptyA, trim5, trim3) : read_fastq(fa, ra, cntA, firstA, trim5, trim3);
 		if(!okA) break;
 		cntA++;
-		if(paired) { bool okB = fasta ? read_fasta(*fbp, rb, cntB, firstB, emptyB) : read_fastq(*fbp, rb, cntB, firstB); if(!okB) break; cntB++; }
+		if(paired) { bool okB = fasta ? read_fasta(*fbp, rb, cntB, firstB, emptyB, trim5, trim3) : read_fastq(*fbp, rb, cntB, firstB, trim5, trim3); if(!okB) break; cntB++; }
 		u32 seedA = gen_rand_seed(ra, 0), seedB = paired ? gen_rand_seed(rb, 0) : 0;
 		bool pair = paired && !rb.seq.empty();
 		bool f1 = n_filter(ra.seq) && ra.seq.size() >= 2, f2 = pair ? (n_filter(rb.seq) && rb.seq.size() >= 2) : false;

@@ -17,11 +17,14 @@ from util_fuzz import clean_reads, mutate_fasta, mutate_fastq
 N_CASES = 200
 
 
+TRIMS = [(0, 0), (0, 0), (3, 0), (0, 5), (4, 7), (90, 0), (0, 200)]
+
+
 def _case(case, seed0):
     rng = random.Random(seed0 + case)
     sub = rng.sample(clean_reads(), 12)
     fasta = case % 2 == 1
-    return fasta, (mutate_fasta(rng, sub) if fasta else mutate_fastq(rng, sub))
+    return fasta, (mutate_fasta(rng, sub) if fasta else mutate_fastq(rng, sub)), TRIMS[rng.randrange(len(TRIMS))]
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref reference binaries not shipped")
@@ -29,9 +32,10 @@ def test_oracle_file_driver_matches_reference_on_irregular_text(tmp_path):
     util.ensure_oracle()
     base = util.golden_index("adv")
 
-    def run(exe, fmt, path, tag):
+    def run(exe, fmt, path, tag, trims):
         tsv, rep = str(tmp_path / (tag + ".tsv")), str(tmp_path / (tag + ".rep"))
-        p = subprocess.run([exe, fmt, "-x", base, "-U", path, "-S", tsv, "--report-file", rep], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        p = subprocess.run([exe, fmt, "-x", base, "-U", path, "-S", tsv, "--report-file", rep, "-5", str(trims[0]), "-3", str(trims[1])],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
         msgs = [l for l in p.stderr.decode(errors="replace").splitlines() if l.startswith("Error") or l.startswith("Saw ASCII")]
         if p.returncode != 0:
             return ("fail", msgs)
@@ -39,12 +43,12 @@ def test_oracle_file_driver_matches_reference_on_irregular_text(tmp_path):
             return ("ok", f.read(), g.read())
 
     for case in range(N_CASES):
-        fasta, data = _case(case, 1000)
+        fasta, data, trims = _case(case, 1000)
         path = str(tmp_path / "in.txt")
         with open(path, "wb") as f:
             f.write(data)
         fmt = "-f" if fasta else "-q"
-        assert run(util.REF_CLASS, fmt, path, "ref") == run(util.ORACLE_BIN, fmt, path, "ora"), (case, fmt)
+        assert run(util.REF_CLASS, fmt, path, "ref", trims) == run(util.ORACLE_BIN, fmt, path, "ora", trims), (case, fmt, trims)
 
 
 def test_product_reader_matches_oracle_reader_on_irregular_text(tmp_path):
@@ -52,16 +56,17 @@ def test_product_reader_matches_oracle_reader_on_irregular_text(tmp_path):
     base = util.golden_index("adv")
     lib = C.CDLL(os.path.join(util.ROOT, "centrifuge_b200", "libcfb200.so"))
     for case in range(N_CASES):
-        fasta, data = _case(case, 5000)
+        fasta, data, trims = _case(case, 5000)
         path, prod, ora = str(tmp_path / "in.txt"), str(tmp_path / "prod.txt"), str(tmp_path / "ora.txt")
         with open(path, "wb") as f:
             f.write(data)
-        rc = lib.cfb_test_parse(path.encode(), C.c_int(1 if fasta else 0), C.c_int(0), C.c_int(0), C.c_uint32(0), prod.encode())
+        rc = lib.cfb_test_parse(path.encode(), C.c_int(1 if fasta else 0), C.c_int(trims[0]), C.c_int(trims[1]), C.c_uint32(0), prod.encode())
         if os.path.exists(ora):
             os.remove(ora)
         p = subprocess.run([util.ORACLE_BIN, "-f" if fasta else "-q", "-x", base, "-U", path, "-S", str(tmp_path / "o.tsv"),
-                            "--report-file", str(tmp_path / "o.rep"), "--dump-reads", ora], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        assert (rc != 0) == (p.returncode != 0), case
+                            "--report-file", str(tmp_path / "o.rep"), "--dump-reads", ora, "-5", str(trims[0]), "-3", str(trims[1])],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert (rc != 0) == (p.returncode != 0), (case, trims)
         if rc == 0:
             with open(prod, "rb") as f, open(ora, "rb") as g:
-                assert f.read() == g.read(), case
+                assert f.read() == g.read(), (case, trims)
