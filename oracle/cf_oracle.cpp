@@ -1140,9 +1140,14 @@ extern "C" int cfo_main(int argc, const char** argv) {
 	while(true) {
 		bool okA, emptyA = false, emptyB = false;
 		okA = fasta ? read_fasta(fa, ra, cntA, firstA, emptyA, trim5, trim3) : read_fastq(fa, ra, cntA, firstA, trim5, trim3);
+		if(paired) {      // both mates are always attempted; a file running out first is an error (pat.cpp:330-420)
+			const bool okB = fasta ? read_fasta(*fbp, rb, cntB, firstB, emptyB, trim5, trim3) : read_fastq(*fbp, rb, cntB, firstB, trim5, trim3);
+			if(!okA && okB) { fprintf(stderr, "Error, fewer reads in file specified with -1 than in file specified with -2\n"); exit(1); }
+			if(okA && !okB) { fprintf(stderr, "Error, fewer reads in file specified with -2 than in file specified with -1\n"); exit(1); }
+			if(okB) cntB++;
+		}
 		if(!okA) break;
 		cntA++;
-		if(paired) { bool okB = fasta ? read_fasta(*fbp, rb, cntB, firstB, emptyB, trim5, trim3) : read_fastq(*fbp, rb, cntB, firstB, trim5, trim3); if(!okB) break; cntB++; }
 		u32 seedA = gen_rand_seed(ra, 0), seedB = paired ? gen_rand_seed(rb, 0) : 0;
 		bool pair = paired && !rb.seq.empty();
 		bool f1 = n_filter(ra.seq) && ra.seq.size() >= 2, f2 = pair ? (n_filter(rb.seq) && rb.seq.size() >= 2) : false;

@@ -51,6 +51,38 @@ def test_oracle_file_driver_matches_reference_on_irregular_text(tmp_path):
         assert run(util.REF_CLASS, fmt, path, "ref", trims) == run(util.ORACLE_BIN, fmt, path, "ora", trims), (case, fmt, trims)
 
 
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref reference binaries not shipped")
+def test_oracle_file_driver_matches_reference_on_irregular_mate_files(tmp_path):
+    """Paired input: independently mutated mate files, including the ones that fall out of step
+    ("fewer reads in file specified with -1/-2": same message, failing exit status)."""
+    util.ensure_oracle()
+    base = util.golden_index("adv")
+    reads = clean_reads()
+
+    def run(exe, fmt, p1, p2, tag):
+        tsv, rep = str(tmp_path / (tag + ".tsv")), str(tmp_path / (tag + ".rep"))
+        p = subprocess.run([exe, fmt, "-x", base, "-1", p1, "-2", p2, "-S", tsv, "--report-file", rep], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        msgs = [l for l in p.stderr.decode(errors="replace").splitlines() if l.startswith("Error") or l.startswith("Saw ASCII")]
+        if p.returncode != 0:
+            return ("fail", msgs)
+        with open(tsv, "rb") as f, open(rep, "rb") as g:
+            return ("ok", f.read(), g.read())
+
+    for case in range(100):
+        rng = random.Random(424200 + case)
+        sub = rng.sample(reads, rng.randrange(1, 10))
+        sub2 = [(n, s[::-1]) for n, s in sub]
+        fasta = rng.random() < 0.5
+        mut = mutate_fasta if fasta else mutate_fastq
+        p1, p2 = str(tmp_path / "a.txt"), str(tmp_path / "b.txt")
+        with open(p1, "wb") as f:
+            f.write(mut(rng, sub))
+        with open(p2, "wb") as f:
+            f.write(mut(rng, sub2))
+        fmt = "-f" if fasta else "-q"
+        assert run(util.REF_CLASS, fmt, p1, p2, "ref") == run(util.ORACLE_BIN, fmt, p1, p2, "ora"), (case, fmt)
+
+
 def test_product_reader_matches_oracle_reader_on_irregular_text(tmp_path):
     util.ensure_oracle()
     base = util.golden_index("adv")
