@@ -938,6 +938,54 @@ extern "C" int cfb_test_parse(const char* path, int fasta, int trim5, int trim3,
 	return rc;
 }
 
+// Test hook (host only): everything cfb_run does around the device call on its record-level path -- reader, batch
+// assembly, seeds and filters, tie selection, TSV rows, per-taxon metrics, EM, report, Kraken-style report -- with the
+// classification records supplied by the caller (tests pass the oracle's), so the whole host side is checked
+// against the reference without a GPU.  rec_off/recs follow cfb_result; units are reads or pairs in file order.
+extern "C" int cfb_test_host_path(const char* index_base, const char* reads_a, const char* reads_b, int fasta, int khits, uint32_t seed,
+                                  int trim5, int trim3, const uint32_t* rec_off, const cfb_rec* recs, uint64_t n_units,
+                                  const char* out_tsv, const char* out_report, const char* out_kreport) {
+	if(!index_base || !reads_a || !rec_off || !out_tsv || !out_report) return CFB_EINVAL;
+	init_tables();
+	cfb_index* ix = NULL;
+	if(cfb_index_load(index_base, -1, &ix) != CFB_OK) return CFB_EIO;
+	int rc = CFB_OK;
+	try {
+		Options o; cfb_params_default(&o.prm);
+		o.prm.khits = khits; o.fasta = fasta != 0; o.seed = seed; o.trim5 = trim5; o.trim3 = trim3; o.report = out_report;
+		if(out_kreport) o.kreport = out_kreport;
+		const HostIndex& h = *cfb_index_host(ix);
+		FileIn fa, fb; const bool paired = reads_b != NULL;
+		if(!fa.open(reads_a) || (paired && !fb.open(reads_b))) throw 2;
+		HostBatch hb; hb.clear(paired);
+		bool firstA = true, firstB = true; uint64_t cntA = 0, cntB = 0; Rec ra, rb;
+		for(;;) {
+			const bool okA = o.fasta ? parse_fasta(fa, ra, cntA, firstA, o.trim5, o.trim3) : parse_fastq(fa, ra, cntA, firstA, o.trim5, o.trim3);
+			bool okB = true;
+			if(paired) okB = o.fasta ? parse_fasta(fb, rb, cntB, firstB, o.trim5, o.trim3) : parse_fastq(fb, rb, cntB, firstB, o.trim5, o.trim3);
+			if(!okA && paired && okB) { std::cerr << "Error, fewer reads in file specified with -1 than in file specified with -2" << std::endl; throw 1; }
+			if(!okA) break;
+			if(!okB) { std::cerr << "Error, fewer reads in file specified with -2 than in file specified with -1" << std::endl; throw 1; }
+			hb.add(ra, paired ? &rb : NULL, o.seed);
+		}
+		fa.close(); fb.close();
+		if(hb.n != n_units) throw 3;
+		cfb_result res; res.n_units = n_units; res.n_recs = rec_off[n_units]; res.rec_off = rec_off; res.recs = recs;
+		Species sp; Formatter fmt(h, o, sp); KReport kr(h, o);
+		fmt.format_batch(hb, res);
+		FILE* fo = fopen(out_tsv, "wb");
+		if(!fo) throw 2;
+		fputs("readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n", fo);
+		if(!fmt.out.empty()) fwrite(fmt.out.data(), 1, fmt.out.size(), fo);
+		fclose(fo);
+		if(kr.enabled() && !fmt.out.empty()) kr.consume(fmt.out.data(), fmt.out.size());
+		write_report(h, o, sp, -1);
+		if(kr.enabled()) kr.write();
+	} catch(int e) { rc = e; }
+	cfb_index_free(ix);
+	return rc;
+}
+
 // The host iteration on caller-provided flattened tables (what cfb_run uses for small tables); same contract as
 // cfb_em_abundance, no device involved.
 extern "C" int cfb_em_abundance_host(uint64_t n, uint64_t K, const uint64_t* count, const uint64_t* key_off, const uint32_t* target,

@@ -197,6 +197,11 @@ int cfb_test_resolve(const cfb_index*, const uint64_t* rows, uint64_t n, uint32_
 /* Host-only test hook: the record-level FASTA/FASTQ reader of cfb_run over a file; one line per read
  * "name<TAB>bases<TAB>seed<TAB>passes filters".  Returns 1 where the reference would stop with an error. */
 int cfb_test_parse(const char* path, int fasta, int trim5, int trim3, uint32_t seed, const char* out_path);
+/* Host-only test hook: the whole host side of the record-level path (reader, seeds, filters, tie selection, rows,
+ * metrics, EM, report, Kraken-style report) around classification records supplied by the caller. */
+int cfb_test_host_path(const char* index_base, const char* reads_a, const char* reads_b, int fasta, int khits, uint32_t seed,
+                       int trim5, int trim3, const uint32_t* rec_off, const cfb_rec* recs, uint64_t n_units,
+                       const char* out_tsv, const char* out_report, const char* out_kreport);
 
 const char* cfb_last_error(void);
 const char* cfb_version(void);
