@@ -14,7 +14,7 @@ from util_em import em_python, random_problem
 def test_host_em_is_bit_identical_to_the_sequential_loops(seed, n, K):
     count, key_off, target, length, p0 = random_problem(seed, n, K)
     want, want_it, want_diff = em_python(count, key_off, target, length, list(p0))
-    lib = C.CDLL(os.path.join(util.ROOT, "centrifuge_b200", "libcfb200.so"))
+    lib = C.CDLL(util.PRODUCT_LIB)
     a_count = np.array(count, dtype=np.uint64); a_off = np.array(key_off, dtype=np.uint64); a_tgt = np.array(target, dtype=np.uint32)
     a_len = np.array(length, dtype=np.uint64); a_p = np.array(p0, dtype=np.float64)
     iters = C.c_uint64(); diff = C.c_double()

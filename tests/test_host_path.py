@@ -39,7 +39,7 @@ def write_reads(path, rs, fasta, rng):
 def test_host_side_reproduces_reference_bytes_around_oracle_records(tmp_path):
     util.ensure_oracle()
     base = util.golden_index("adv")
-    lib = C.CDLL(os.path.join(util.ROOT, "centrifuge_b200", "libcfb200.so"))
+    lib = C.CDLL(util.PRODUCT_LIB)
     reads = clean_reads()
     o = util.Oracle(base)
     for case in range(200):

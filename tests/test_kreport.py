@@ -14,7 +14,7 @@ CASES = [("default", "", (0, 0, 0, 0, 0)), ("default", ".zeros", (1, 0, 0, 0, 0)
 
 
 def lib():
-    return C.CDLL(os.path.join(util.ROOT, "centrifuge_b200", "libcfb200.so"))
+    return C.CDLL(util.PRODUCT_LIB)
 
 
 @pytest.mark.parametrize("case,suffix,args", CASES)

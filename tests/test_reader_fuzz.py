@@ -86,7 +86,7 @@ def test_oracle_file_driver_matches_reference_on_irregular_mate_files(tmp_path):
 def test_product_reader_matches_oracle_reader_on_irregular_text(tmp_path):
     util.ensure_oracle()
     base = util.golden_index("adv")
-    lib = C.CDLL(os.path.join(util.ROOT, "centrifuge_b200", "libcfb200.so"))
+    lib = C.CDLL(util.PRODUCT_LIB)
     for case in range(N_CASES):
         fasta, data, trims = _case(case, 5000)
         path, prod, ora = str(tmp_path / "in.txt"), str(tmp_path / "prod.txt"), str(tmp_path / "ora.txt")

@@ -21,6 +21,7 @@ REF_BUILD = os.path.join(REFDIR, "centrifuge-build-bin")
 ORACLE_BIN = os.path.join(REFDIR, "cf_oracle")
 ORACLE_LIB = os.path.join(REFDIR, "libcforacle.so")
 HOSTLOGIC_LIB = os.environ.get("CFB_HOSTLOGIC_LIB", os.path.join(REFDIR, "libhostlogic.so"))   # override: a sanitizer build of the shim
+PRODUCT_LIB = os.environ.get("CFB_PRODUCT_LIB", os.path.join(ROOT, "centrifuge_b200", "libcfb200.so"))   # override: sanitizer build of the host side (tests/native/host_stub.cpp)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 CACHE = os.environ.get("CFB_TEST_CACHE", os.path.join(tempfile.gettempdir(), "cfb200_test_cache"))
 
