@@ -1110,6 +1110,7 @@ extern "C" int cfb_run(int argc, const char** argv) {
 				if(at == 0) return;
 				f.seek(at); first = false;
 				if(!o.fasta) { while(f.peek() == '\n' || f.peek() == '\r') f.get(); f.get(); }   // the '@' that ends the previous record's parse
+				else { while(f.peek() >= 0 && f.peek() != '>') f.get(); }   // the previous record's sequence loop runs up to the next '>' (blank lines at a span start belong to it)
 			};
 			resume(fa, off[0], firstA);
 			if(srcs[si].paired) resume(fb, off[1], firstB);
