@@ -42,26 +42,29 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------ workload
+PREFIX = "cid"      # sequence names cid<i>: >= 10 of them make the index a "compressed" one (ihits = 20, bt2_idx.h:648-663), as p_compressed is
+
+
 def synth_opts(genera, species, length, seed, base=None, device=0, tax=None):
     from centrifuge_b200 import capi
     kw = {}
     if tax:
         kw = dict(conversion_table=tax[0], taxonomy_tree=tax[1], name_table=tax[2])
-    return capi.build_opts(base, synth=(genera, species, length, seed, 0.03), device=device, **kw)
+    return capi.build_opts(base, synth=(genera, species, length, seed, 0.03), device=device, synth_prefix=PREFIX, **kw)
 
 
 def get_index(genera, species, length, seed, device=0):
     """Synthetic p_compressed-class index on local disk, built once per box by the GPU builder
     (centrifuge_b200/csrc/cf_build.cu; byte-identical to centrifuge-build-bin, tests/test_gpu_build.py)."""
     from centrifuge_b200 import capi
-    tag = "g%d_s%d_l%d_seed%d" % (genera, species, length, seed)
+    tag = "%s_g%d_s%d_l%d_seed%d" % (PREFIX, genera, species, length, seed)
     d = os.path.join(CACHE, tag)
     base = os.path.join(d, "idx")
     if os.path.exists(os.path.join(d, "done")):
         return base, d
     os.makedirs(d, exist_ok=True)
     t0 = time.time()
-    tax = capi.write_synth_taxonomy(d, genera, species, length)
+    tax = capi.write_synth_taxonomy(d, genera, species, length, prefix=PREFIX)
     capi.build_index(synth_opts(genera, species, length, seed, base, device, tax))
     open(os.path.join(d, "done"), "w").close()
     log("index %s built on the GPU in %.1f s" % (tag, time.time() - t0))
@@ -203,6 +206,58 @@ class RefArm:
         return max(t2 - t1, 1e-6), self.n - self.n_small
 
 
+def parity_check(a, ctx, ix, base, d, codes, nsample):
+    """Un-timed: the first `nsample` reads of this run's own batch, classified by the *same* context the timed loops
+    use (every derived table live), against the unmodified reference binary on the same index and the same FASTQ:
+    (1) the TSV the text operator returns must equal the reference's bytes, (2) the records the C ABI returns must
+    be the rows of that TSV (per read: the records with the best score <-> the rows, taxID / score / hitLength)."""
+    from centrifuge_b200 import capi
+    import pandas as pd
+    tb = ix.tables()
+    tables = {"ftabk": tb["ftabk_chars"], "rtab": 8 * tb["resolve_entry_bytes"], "walk8": tb["walk8_bytes"] > 0,
+              "compressed": bool(ix.info.compressed), "rows_beyond_2^32": bool(ix.info.len >= (1 << 32))}
+    if not os.path.exists(REF_CLASS):
+        return {"reads": 0, "identical": None, "tables": tables, "skipped": "oracle/_ref/centrifuge-class not shipped"}
+    sub = codes[:nsample]
+    n, L = sub.shape
+    fm = fastq_matrix(sub)
+    fq, ref_tsv = os.path.join(d, "parity_%d.fq" % os.getpid()), os.path.join(d, "parity_%d.tsv" % os.getpid())
+    with open(fq, "wb") as f:
+        f.write(fm.tobytes())
+    p = min(16, os.cpu_count() or 1)
+    t0 = time.time()
+    subprocess.check_call([REF_CLASS, "-q", "-x", base, "-U", fq, "-p", str(p), "--reorder", "-S", ref_tsv, "--report-file", "/dev/null"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    with open(ref_tsv, "rb") as f:
+        want = f.read()
+    t_ref = time.time() - t0
+    pt = capi.pinned_array((fm.size,), np.uint8); pt[:] = fm.reshape(-1)
+    ctx.text_submit(0, pt, None, n, maxlen_hint=L)
+    r = ctx.text_wait(0, discard=True)
+    header = b"readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n"
+    tsv_ok = (not r["irregular"]) and header + r["tsv"] == want
+    # records of the C ABI against the reference's rows
+    flags = ((sub == 4).sum(axis=1) <= int(0.15 * L)).astype(np.uint8)
+    lens = np.full(n, L, dtype=np.uint32); offs = np.arange(n, dtype=np.uint64) * np.uint64(L)
+    off, recs = ctx.classify(capi.make_batch(np.ascontiguousarray(sub.reshape(-1)), offs, lens, None, None, flags))
+    df = pd.read_csv(ref_tsv, sep="\t", dtype={"readID": str, "seqID": str})
+    rid = df["readID"].str[1:].astype(np.int64).to_numpy()
+    cls = (df["seqID"] != "unclassified").to_numpy()
+    rows = np.stack([rid[cls], df["taxID"].to_numpy(np.int64)[cls], df["score"].to_numpy(np.int64)[cls], df["hitLength"].to_numpy(np.int64)[cls]], axis=1)
+    cnt = np.diff(off.astype(np.int64))
+    unit = np.repeat(np.arange(n), cnt)
+    best = np.zeros(n, dtype=np.int64)
+    np.maximum.at(best, unit, recs["score"].astype(np.int64))
+    top = recs["score"].astype(np.int64) == best[unit]
+    mine = np.stack([unit[top], recs["taxid"][top].astype(np.int64), recs["score"][top].astype(np.int64), recs["hitlen"][top].astype(np.int64)], axis=1)
+    key = lambda x: x[np.lexsort((x[:, 3], x[:, 2], x[:, 1], x[:, 0]))]
+    rec_ok = mine.shape == rows.shape and bool(np.array_equal(key(mine), key(rows)))
+    uncl_ok = bool(np.array_equal(np.sort(rid[~cls]), np.nonzero(cnt == 0)[0]))
+    os.unlink(fq); os.unlink(ref_tsv)
+    return {"reads": int(n), "identical": bool(tsv_ok and rec_ok and uncl_ok), "tsv_bytes_identical": bool(tsv_ok), "abi_records_match_rows": bool(rec_ok and uncl_ok),
+            "tables": tables, "rows": int(len(df)), "reference": "oracle/_ref/centrifuge-class -p %d --reorder, same index, same FASTQ (%.1f s)" % (p, t_ref)}
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -237,6 +292,7 @@ def _main(result):
     ap.add_argument("--reads", type=int, default=int(os.environ.get("CFB_BENCH_READS", 2000000)), help="reads per step per GPU")
     ap.add_argument("--rdlen", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("CFB_BENCH_CPU_SAMPLE", 400000)))
+    ap.add_argument("--parity-reads", type=int, default=int(os.environ.get("CFB_BENCH_PARITY_READS", 200000)), help="reads of the step batch checked against the reference binary (un-timed)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     ncores = os.cpu_count() or 1
@@ -307,6 +363,12 @@ def _main(result):
         if dist:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # ---------------- un-timed parity check of the configuration being timed (rank 0; the other ranks wait at the barrier)
+    parity = None
+    if rank == 0:
+        parity = parity_check(a, ctx, ix, base, d, codes, min(a.parity_reads, n))
+        log("parity check: %s" % json.dumps(parity))
 
     # ---------------- un-timed counter pass (algorithmic bytes of this exact batch)
     os.environ["CFB_COUNT"] = "1"
@@ -467,7 +529,9 @@ def _main(result):
         "clocks": sampler.summary(),
         "taxon_vector": {"len": int(counts.numel()), "classified_reads_rank0": int(local_counts[:-1, 0].sum()), "unclassified_reads_rank0": int(local_counts[-1, 1])},
         "wall_s_value_region": wall_s,
+        "parity_check": parity,
     }
+    out["config"]["tables"] = {k: v for k, v in ix.tables().items()}
     if numa is not None:
         out["config"]["numa_node"] = numa
     if rank == 0 and world > 1:
@@ -486,6 +550,9 @@ def _main(result):
     ctx.close(); ix.close()
     if dist:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and parity.get("identical") is False:
+        log("PARITY CHECK FAILED: the timed configuration does not reproduce the reference's output")
+        return 3
     return 0
 
 

@@ -27,6 +27,11 @@ class IndexInfo(C.Structure):
                 ("sample_bytes", C.c_int32), ("compressed", C.c_int32), ("device", C.c_int32), ("device_bytes", C.c_uint64)]
 
 
+class IndexTables(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("sides_bytes", "sample_bytes", "rank16_bytes", "ftab2_bytes", "ftabk_bytes", "resolve_table_bytes",
+                                          "walk8_bytes", "total_bytes", "free_bytes_after_load")] + [("ftabk_chars", C.c_int32), ("resolve_entry_bytes", C.c_int32)]
+
+
 class Params(C.Structure):
     _fields_ = [("khits", C.c_int32), ("min_hitlen", C.c_int32), ("tree_traverse", C.c_int32), ("class_rank_slot", C.c_int32),
                 ("host_taxids", C.POINTER(C.c_uint64)), ("n_host_taxids", C.c_uint64),
@@ -68,11 +73,17 @@ def _p(a, t):
 
 
 class Index:
-    def __init__(self, basename, device=0):
+    def __init__(self, basename, device=0, flags=0):
         self.h = C.c_void_p()
-        _ck(lib().cfb_index_load(basename.encode(), C.c_int(device), C.byref(self.h)))
+        _ck(lib().cfb_index_load_ex(basename.encode(), C.c_int(device), C.c_uint32(flags), C.byref(self.h)))
         self.info = IndexInfo()
         _ck(lib().cfb_index_get_info(self.h, C.byref(self.info)))
+
+    def tables(self):
+        """dict of what the device replica holds (cfb_index_get_tables)"""
+        t = IndexTables()
+        _ck(lib().cfb_index_get_tables(self.h, C.byref(t)))
+        return {n: int(getattr(t, n)) for n, _ in IndexTables._fields_}
 
     def seq_name(self, i):
         s = lib().cfb_index_seq_name(self.h, C.c_uint32(i))
@@ -258,11 +269,12 @@ class BuildOpts(C.Structure):
     _fields_ = [("out_base", C.c_char_p), ("fasta", C.POINTER(C.c_char_p)), ("n_fasta", C.c_int32),
                 ("synth_genera", C.c_uint32), ("synth_species", C.c_uint32), ("synth_len", C.c_uint64), ("synth_seed", C.c_uint64),
                 ("synth_div", C.c_double), ("conversion_table", C.c_char_p), ("taxonomy_tree", C.c_char_p), ("name_table", C.c_char_p),
-                ("size_table", C.c_char_p), ("ftab_chars", C.c_int32), ("off_rate", C.c_int32), ("device", C.c_int32), ("verbose", C.c_int32)]
+                ("size_table", C.c_char_p), ("ftab_chars", C.c_int32), ("off_rate", C.c_int32), ("device", C.c_int32), ("verbose", C.c_int32),
+                ("synth_prefix", C.c_char_p)]
 
 
 def build_opts(out_base=None, fasta=(), synth=None, conversion_table=None, taxonomy_tree=None, name_table=None, size_table=None,
-               ftab_chars=10, off_rate=4, device=0, verbose=0):
+               ftab_chars=10, off_rate=4, device=0, verbose=0, synth_prefix=None):
     """synth = (genera, species, len, seed, div) for counter-based synthetic genomes."""
     o = BuildOpts()
     lib().cfb_build_opts_default(C.byref(o))
@@ -276,6 +288,8 @@ def build_opts(out_base=None, fasta=(), synth=None, conversion_table=None, taxon
         if v:
             setattr(o, k, v.encode())
     o.ftab_chars, o.off_rate, o.device, o.verbose = ftab_chars, off_rate, device, verbose
+    if synth_prefix:
+        o.synth_prefix = synth_prefix.encode()
     return o
 
 
@@ -303,13 +317,13 @@ def synth_fasta(opts, path):
         raise CfbError("cfb_synth_fasta failed")
 
 
-def write_synth_taxonomy(outdir, genera, species, length):
+def write_synth_taxonomy(outdir, genera, species, length, prefix="seq"):
     """conversion table / nodes.dmp / names.dmp of the synthetic recipe (same as tools/synth.py)."""
     os.makedirs(outdir, exist_ok=True)
     n = genera * species
     with open(os.path.join(outdir, "conv.tsv"), "w") as f:
         for i in range(n):
-            f.write("seq%d\t%d\n" % (i, 1000 + i))
+            f.write("%s%d\t%d\n" % (prefix, i, 1000 + i))
     with open(os.path.join(outdir, "nodes.dmp"), "w") as f:
         f.write("1\t|\t1\t|\tno rank\t|\n")
         for g in range(genera):

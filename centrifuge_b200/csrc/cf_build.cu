@@ -439,7 +439,7 @@ extern "C" int cfb_build_index(const cfb_build_opts* o) {
 		sp.div_q32 = (uint32_t)std::min(4294967295.0, o->synth_div * 4294967296.0);
 		std::vector<Rec> recs; std::vector<std::string> names;
 		const uint32_t ns = sp.genera * sp.species;
-		for(uint32_t i = 0; i < ns; i++) { Rec r = {0, sp.len, true}; recs.push_back(r); char b[32]; snprintf(b, sizeof b, "seq%u", i); names.push_back(b); }
+		for(uint32_t i = 0; i < ns; i++) { Rec r = {0, sp.len, true}; recs.push_back(r); char b[64]; snprintf(b, sizeof b, "%.40s%u", o->synth_prefix ? o->synth_prefix : "seq", i); names.push_back(b); }
 		build_meta(recs, names, m);
 	} else {
 		std::vector<std::string> files; for(int i = 0; i < o->n_fasta; i++) files.push_back(o->fasta[i]);
@@ -774,7 +774,7 @@ extern "C" int cfb_synth_fasta(const cfb_build_opts* o, const char* path) {
 	if(!f) return bfail(CFB_EIO, "cannot write %s", path);
 	std::string line;
 	for(uint32_t s = 0; s < sp.genera * sp.species; s++) {
-		fprintf(f, ">seq%u\n", s);
+		fprintf(f, ">%.40s%u\n", o->synth_prefix ? o->synth_prefix : "seq", s);
 		for(uint64_t p = 0; p < sp.len; p += 80) {
 			line.clear();
 			for(uint64_t q = p; q < std::min(sp.len, p + 80); q++) line.push_back("ACGT"[synth_base(sp, s, q)]);

@@ -606,9 +606,12 @@ struct SpanFile {        // one input file of a source, consumed in spans that e
 	int fd = -1; uint64_t file_pos = 0, file_size = 0, span_start = 0; bool eof = false;
 	std::vector<unsigned char> carry;              // bytes after the previous cut
 	bool open(const std::string& p) {
+		// stat before open: opening and closing a FIFO (the `centrifuge` wrapper feeds compressed reads through mkfifo,
+		// centrifuge:470-545) would leave its writer without a reader
+		struct stat st; if(::stat(p.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) return false;
 		fd = ::open(p.c_str(), O_RDONLY);
 		if(fd < 0) return false;
-		struct stat st; if(fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); fd = -1; return false; }
+		if(fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { ::close(fd); fd = -1; return false; }
 		file_size = (uint64_t)st.st_size;
 		posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
 		return true;
@@ -649,6 +652,12 @@ struct SpanFile {        // one input file of a source, consumed in spans that e
 		if(eof && n > 0 && buf[n - 1] != '\n') { buf[n++] = '\n'; nl++; }    // last line without a line end
 		*lines = nl;
 		return n;
+	}
+	// the byte that follows the last cut (first carried byte, else the next file byte); -1 at the end of the input
+	int next_byte() const {
+		if(!carry.empty()) return carry[0];
+		if(file_pos >= file_size) return -1;
+		unsigned char c; return pread(fd, &c, 1, (off_t)file_pos) == 1 ? (int)c : -1;
 	}
 	// keep the first `keep_lines` lines of buf[0..n): returns the cut, stores the rest as carry
 	size_t cut(const unsigned char* buf, size_t n, size_t lines, size_t keep_lines) {
@@ -733,6 +742,21 @@ struct TextPipe {
 				sp.start[0] = f[0].span_start; sp.start[1] = paired ? f[1].span_start : 0; sp.irregular = irregular; sp.rec = rec;
 				if(!irregular) {
 					for(int m = 0; m < nm; m++) sp.bytes[m] = f[m].cut(buf[m][s], n[m], lines[m], rec * L);
+					// A FASTA record runs up to the next '>' (pat.cpp:806-826), so its last line inside the span need not be
+					// its end: unless the byte after the cut is '>' (or the input ends there), the tail record may continue in
+					// the next span and is carried over whole; the wrapped record then sits inside one span, where the strict
+					// layout check sees it and hands over to the record-level reader.
+					if(o.fasta) {
+						bool open_tail = false;
+						for(int m = 0; m < nm; m++) { const int nb = f[m].next_byte(); if(nb >= 0 && nb != '>') open_tail = true; }
+						if(open_tail) {
+							rec -= 1; sp.rec = rec;
+							if(rec == 0) { irregular = true; sp.irregular = true; }
+							else for(int m = 0; m < nm; m++) sp.bytes[m] = f[m].cut(buf[m][s], n[m], lines[m], rec * L);
+						}
+					}
+				}
+				if(!irregular) {
 					if(first) {     // longest line in the head of the file sizes the first pass
 						first = false; size_t longest = 0, ls = 0; const size_t lim = std::min<size_t>(sp.bytes[0], 1u << 16);
 						for(size_t i = 0; i < lim; i++) if(buf[0][s][i] == '\n') { longest = std::max(longest, i - ls); ls = i + 1; }

@@ -1304,6 +1304,8 @@ struct cfb_index {
 	std::vector<void*> dptrs;
 	uint64_t device_bytes = 0;
 	int sm_count = 0;
+	cfb_index_tables tables;
+	cfb_index() { memset(&tables, 0, sizeof tables); }
 };
 
 static int upload(cfb_index* ix, const void* src, size_t bytes, const void** dst) {
@@ -1372,6 +1374,7 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 		int rc;
 		#define UP(field, vec, T) if((rc = upload(ix, (vec).data(), (vec).size() * sizeof(T), (const void**)&v.field)) != CFB_OK) { cfb_index_free(ix); return rc; }
 		if((rc = stream_to_device(ix, std::string(basename) + ".1.cf", h.sides_file_off, h.num_sides * h.side_sz, (const void**)&v.sides)) != CFB_OK) { cfb_index_free(ix); return rc; }
+		ix->tables.sides_bytes = h.num_sides * h.side_sz; ix->tables.sample_bytes = h.offs_len * (h.wide_sample ? 4 : 2);
 		UP(ftab, h.ftab, uint64_t) UP(eftab, h.eftab, uint64_t)
 		if((rc = stream_to_device(ix, std::string(basename) + ".2.cf", h.sample_file_off, h.offs_len * (h.wide_sample ? 4 : 2),
 		                          h.wide_sample ? (const void**)&v.sample32 : (const void**)&v.sample16)) != CFB_OK) { cfb_index_free(ix); return rc; }
@@ -1411,6 +1414,7 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 			k_build_ftab2<<<(unsigned)((nf + 255) / 256), 256>>>(v, nf, f2);
 			CK(cudaDeviceSynchronize());
 			v.rank16 = r16; v.ftab2 = f2;
+			ix->tables.rank16_bytes = (nb + 1) * 64; ix->tables.ftab2_bytes = nf * 16;
 			// extended jump table: K = largest value with 4^K <= len/4 (most K-mers occur), capped at 15 and by free HBM
 			int K = 0;
 			{ const char* e = getenv("CFB_FTABK"); if(e) K = atoi(e); else { K = h.ftab_chars; while(K < 15 && (4ull << (2 * K)) <= h.len / 4) K++; } }
@@ -1423,6 +1427,7 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 				k_build_ftabk<<<(unsigned)((nk + 255) / 256), 256>>>(v, K, nk, fk);
 				CK(cudaDeviceSynchronize());
 				v.ftabk = fk; v.ftabk_chars = K;
+				ix->tables.ftabk_bytes = nk * 16; ix->tables.ftabk_chars = K;
 			}
 			// resolve table: sequence id of every SA row (walked once here), if it fits comfortably
 			{
@@ -1442,6 +1447,7 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 					CK(cudaDeviceSynchronize());
 					cudaFree(sc);
 					if(h.wide_sample) v.rtab32 = (const uint32_t*)tab; else v.rtab16 = (const uint16_t*)tab;
+					ix->tables.resolve_table_bytes = nrows * esz; ix->tables.resolve_entry_bytes = (int32_t)esz;
 				}
 			}
 			// walk8: eight single-row LF steps per gather, if 8 bytes per row still leave room for the batch buffers
@@ -1457,9 +1463,11 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 					k_build_walk8<<<prop.multiProcessorCount * std::max(occ, 1) * 4, kSearchThreads>>>(v, nrows, (uint64_t*)tab);
 					CK(cudaDeviceSynchronize());
 					v.walk8 = (const uint64_t*)tab;
+					ix->tables.walk8_bytes = nrows * 8;
 				}
 			}
 		}
+		{ size_t fb = 0, tb = 0; cudaMemGetInfo(&fb, &tb); ix->tables.total_bytes = ix->device_bytes; ix->tables.free_bytes_after_load = fb; }
 		// host copies of the big arrays are no longer needed once uploaded
 		std::vector<uint8_t>().swap(ix->h.sides);
 	}
@@ -1478,6 +1486,11 @@ extern "C" int cfb_index_get_info(const cfb_index* ix, cfb_index_info* o) {
 	o->len = h.len; o->num_sides = h.num_sides; o->n_seqs = h.seq_taxid.size(); o->n_tax_nodes = h.nodes.size();
 	o->n_boundaries = h.brow.size(); o->line_rate = h.line_rate; o->off_rate = h.off_rate; o->ftab_chars = h.ftab_chars;
 	o->sample_bytes = h.wide_sample ? 4 : 2; o->compressed = h.compressed ? 1 : 0; o->device = ix->device; o->device_bytes = ix->device_bytes;
+	return CFB_OK;
+}
+extern "C" int cfb_index_get_tables(const cfb_index* ix, cfb_index_tables* o) {
+	if(!ix || !o) return fail(CFB_EINVAL, "null argument");
+	*o = ix->tables;
 	return CFB_OK;
 }
 extern "C" const char* cfb_index_seq_name(const cfb_index* ix, uint32_t s) { return (ix && s < ix->h.seq_name.size()) ? ix->h.seq_name[s].c_str() : NULL; }

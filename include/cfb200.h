@@ -65,6 +65,17 @@ typedef struct {
 } cfb_index_info;
 int cfb_index_get_info(const cfb_index*, cfb_index_info* out);
 
+/* What the device replica holds (bytes of HBM each; 0 = not built).  The derived tables are built at load time in
+ * this order of benefit per byte, each only while it fits the budget left after the batch head-room:
+ * rank16 + ftab2 (always), the K-mer jump table, the resolve table, walk8. */
+typedef struct {
+	uint64_t sides_bytes, sample_bytes, rank16_bytes, ftab2_bytes, ftabk_bytes, resolve_table_bytes, walk8_bytes;
+	uint64_t total_bytes, free_bytes_after_load;
+	int32_t  ftabk_chars;           /* K of the jump table, 0 = none */
+	int32_t  resolve_entry_bytes;   /* 2 or 4, 0 = no resolve table (rows are resolved by walking) */
+} cfb_index_tables;
+int cfb_index_get_tables(const cfb_index*, cfb_index_tables* out);
+
 /* Taxonomy accessors the host formatter needs (Ebwt::uid_to_tid/tree/name/size). */
 const char* cfb_index_seq_name(const cfb_index*, uint32_t seq);           /* uid string */
 uint64_t    cfb_index_seq_taxid(const cfb_index*, uint32_t seq);
@@ -222,6 +233,8 @@ typedef struct {
 	const char* size_table;         /* --size-table, may be NULL */
 	int32_t ftab_chars, off_rate;   /* defaults 10, 4 (centrifuge_build.cpp:93-97) */
 	int32_t device, verbose;
+	const char* synth_prefix;       /* synthetic sequence names are <prefix><i>; NULL = "seq".  "cid" makes the index a
+	                                   "compressed" one for the classifier (>= 10 names starting with cid, bt2_idx.h:648-663) */
 } cfb_build_opts;
 void cfb_build_opts_default(cfb_build_opts*);
 int  cfb_build_index(const cfb_build_opts*);

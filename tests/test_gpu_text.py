@@ -194,3 +194,48 @@ def test_mate_files_out_of_step_report_the_reference_error(syn, tmp_path):
                            stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=dict(os.environ, CFB_TEXT_BLOCK="40000"))
         assert p.returncode != 0
         assert b"fewer reads in file specified with -2" in p.stderr
+
+
+def test_fasta_record_wrapped_across_a_span_cut(syn, tmp_path):
+    """A FASTA record runs up to the next '>' (pat.cpp:806-826): when a span cut falls right after the first sequence
+    line of a wrapped record, the span must not emit that record from its first line alone.  The cut position depends
+    on the span size, so a range of sizes is swept; every one must reproduce the reference's bytes, and the wrapped
+    record must end up with the record-level reader."""
+    base, seqs = syn
+    reads = util.synth.sample_reads(seqs, 1500, 100, seed=41, lens=(60, 140))
+    fa = str(tmp_path / "w.fa")
+    recs = []
+    for i, (name, a) in enumerate(reads):
+        s = a.tobytes()
+        if i >= 700 and i % 2 == 0:          # from the middle of the file on, every other record is wrapped after 30 bases
+            recs.append(b">" + name.encode() + b"\n" + s[:30] + b"\n" + s[30:] + b"\n")
+        else:
+            recs.append(b">" + name.encode() + b"\n" + s + b"\n")
+    with open(fa, "wb") as f:
+        f.write(b"".join(recs))
+    # a file whose only wrapped record is the one a cut can split: spans are cut where the line count allows, so put
+    # the wrapped record at many different byte offsets by sweeping the block size
+    args = ["-f", "-x", base, "-U", fa]
+    want = run_ref(args, tmp_path, "ref")
+    for block in (4096, 5000, 7777, 12345, 20011, 33333):
+        got, st = run_ours(args, tmp_path, "our%d" % block, block=block)
+        assert got == want, block
+        assert st["fallbacks"] == 1 and st["text"] + st["host"] == len(reads), (block, st)
+    # single wrapped record exactly at a cut: strict records of fixed size, so the cut position is known
+    fixed = [(("r%04d" % i), np.frombuffer(b"ACGT" * 20, dtype=np.uint8)) for i in range(600)]
+    for i in range(len(fixed)):
+        fixed[i] = (fixed[i][0], reads[i][1][:80] if len(reads[i][1]) >= 80 else fixed[i][1])
+    rec_bytes = 1 + 5 + 1 + 80 + 1                       # ">r0000\n" + 80 bases + "\n"
+    for split_at in (100, 101):
+        body = []
+        for i, (n, a) in enumerate(fixed):
+            s = a.tobytes()
+            body.append(b">" + n.encode() + b"\n" + (s[:40] + b"\n" + s[40:] if i == split_at else s) + b"\n")
+        with open(fa, "wb") as f:
+            f.write(b"".join(body))
+        want = run_ref(args, tmp_path, "ref2")
+        # a block that ends inside record `split_at`, after its first sequence line
+        block = split_at * rec_bytes + 1 + 5 + 1 + 40 + 1 + 3
+        got, st = run_ours(args, tmp_path, "cut%d" % split_at, block=block)
+        assert got == want, split_at
+        assert st["text"] + st["host"] == len(fixed) and st["host"] >= len(fixed) - split_at - 1, st
