@@ -233,6 +233,42 @@ class Context:
             _ck(lib().cfb_text_species(self.h, *[_p(a, C.c_uint64) for a in arrs], C.c_uint64(k), C.byref(n)))
         return dict(taxid=arrs[0], n_reads=arrs[1], n_unique=arrs[2], n_obs1=arrs[3])
 
+    # ---- per-taxon counters and the multi-GPU reduction
+    def count_records(self, on=True):
+        _ck(lib().cfb_ctx_count_records(self.h, C.c_int(1 if on else 0)))
+
+    def counts_taxids(self):
+        n = C.c_uint64()
+        _ck(lib().cfb_counts_taxids(self.h, None, C.c_uint64(0), C.byref(n)))
+        out = np.zeros(int(n.value), dtype=np.uint64)
+        _ck(lib().cfb_counts_taxids(self.h, _p(out, C.c_uint64), C.c_uint64(len(out)), C.byref(n)))
+        return out
+
+    def counts_reset(self):
+        _ck(lib().cfb_counts_reset(self.h))
+
+    def counts_dense(self, global_=False, n=None):
+        """(3, n) uint64: numReads, numUniqueReads, observed singletons per entry of counts_taxids()"""
+        if n is None:
+            n = len(self.counts_taxids())
+        out = np.zeros(3 * n, dtype=np.uint64)
+        _ck(lib().cfb_counts_dense(self.h, C.c_int(1 if global_ else 0), _p(out, C.c_uint64), C.c_uint64(out.size)))
+        return out.reshape(3, n)
+
+    def comm_init_rank(self, nranks, rank, uid):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))
+        _ck(lib().cfb_comm_init_rank(self.h, C.c_int(nranks), C.c_int(rank), buf))
+
+    def counts_allreduce(self, out=None):
+        """collective over the communicator this context belongs to (a no-op copy without one)"""
+        arr = (C.c_void_p * 1)(self.h)
+        _ck(lib().cfb_counts_allreduce(arr, C.c_int(1), _p(out, C.c_uint64) if out is not None else None, C.c_uint64(out.size if out is not None else 0)))
+
+    def requests(self):
+        out = (C.c_uint64 * 4)()
+        _ck(lib().cfb_ctx_requests(self.h, out))
+        return dict(zip(["rank16", "ftab2", "ftabk", "walk8"], [int(x) for x in out]))
+
     def counters(self):
         out = (C.c_uint64 * 8)()
         _ck(lib().cfb_ctx_counters(self.h, out))
@@ -248,6 +284,29 @@ class Context:
         if self.h:
             lib().cfb_ctx_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def comm_unique_id():
+    buf = (C.c_uint8 * 128)()
+    _ck(lib().cfb_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init_all(contexts):
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    _ck(lib().cfb_comm_init_all(arr, C.c_int(len(contexts))))
+
+
+def counts_allreduce_all(contexts):
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    _ck(lib().cfb_counts_allreduce(arr, C.c_int(len(contexts)), None, C.c_uint64(0)))
+
+
+def gather_ceiling(index, table, n_requests=1 << 30):
+    """G requests/s of independent random gathers over one of the replica's arrays (0 rank16, 1 K-mer table, 2 walk8, 3 resolve table)"""
+    g, ms = C.c_double(), C.c_double()
+    _ck(lib().cfb_gather_ceiling(index.h, C.c_int(table), C.c_uint64(n_requests), C.byref(g), C.byref(ms)))
+    return float(g.value), float(ms.value)
 
 
 def test_lf(index, rows, chars):

@@ -42,6 +42,7 @@ using namespace cfb;
 
 // the loader's HostIndex lives inside cfb_index; the driver only needs these accessors
 extern "C" const cfb::HostIndex* cfb_index_host(const cfb_index*);
+extern "C" int cfb_device_count(void);
 
 namespace {
 
@@ -49,7 +50,7 @@ struct Options {
 	std::string index, out = "-", report = "centrifuge_report.tsv";
 	std::vector<std::string> singles, mates1, mates2;
 	bool fasta = false, abundance = true, quiet = false, time = false;
-	int device = 0;
+	int device = 0; std::vector<int> devices;      // --device N / --devices 0-7: reads are dealt round-robin to the listed GPUs (index replicated)
 	uint64_t skip = 0, upto = std::numeric_limits<uint64_t>::max();
 	uint32_t seed = 0;
 	size_t batch_units = 1u << 18;
@@ -65,7 +66,7 @@ static const OptDesc kLong[] = {
 	{"quiet", 0}, {"time", 0}, {"seed", 1}, {"upto", 1}, {"qupto", 1}, {"skip", 1}, {"version", 0}, {"help", 0}, {"threads", 1},
 	{"reorder", 0}, {"mm", 0}, {"wrapper", 1}, {"arg-desc", 0}, {"report-file", 1}, {"no-abundance", 0}, {"no-traverse", 0},
 	{"min-hitlen", 1}, {"host-taxids", 1}, {"exclude-taxids", 1}, {"classification-rank", 1}, {"trim5", 1}, {"trim3", 1},
-	{"device", 1}, {"batch-units", 1}, {"text-block-mb", 1}, {"host-parse", 0},
+	{"device", 1}, {"devices", 1}, {"batch-units", 1}, {"text-block-mb", 1}, {"host-parse", 0},
 	{"kreport-file", 1}, {"kreport-show-zeros", 0}, {"kreport-min-score", 1}, {"kreport-min-length", 1}, {NULL, 0}};
 static const char* kShort = "fqtu:s:p:k:1:2:U:x:S:3:5:h";
 
@@ -686,33 +687,37 @@ template <class T> struct Chan {        // small blocking queue between the pipe
 };
 
 // Three threads per source: a reader that fills pinned buffers and cuts spans at record boundaries, this
-// thread submitting spans to the device and collecting them in order, and a writer for the rows.
+// thread submitting spans to the device(s) and collecting them in order, and a writer for the rows.  With several
+// devices (--devices) span k goes to device k mod N: every device holds a replica of the index and its own context,
+// spans are collected in submission order, so the output is the one-device output byte for byte.
 struct TextPipe {
-	cfb_ctx* ctx; const Options& o; FILE* fo; MultiObs& multi; TextStats& st; KReport* kr = NULL;
-	int nslots = 0; size_t cap = 0; int read_threads = 8;
+	std::vector<cfb_ctx*> ctxs; const Options& o; FILE* fo; MultiObs& multi; TextStats& st; KReport* kr = NULL;
+	int S = 4; size_t cap = 0; int read_threads = 8;       // S spans per device: reader + 2 on the device + writer
 	std::vector<unsigned char*> buf[2];
-	TextPipe(cfb_ctx* c, const Options& o_, FILE* f, MultiObs& m, TextStats& s) : ctx(c), o(o_), fo(f), multi(m), st(s) {
+	TextPipe(const std::vector<cfb_ctx*>& c, const Options& o_, FILE* f, MultiObs& m, TextStats& s) : ctxs(c), o(o_), fo(f), multi(m), st(s) {
 		const unsigned hw = std::thread::hardware_concurrency();
 		if(hw) read_threads = (int)std::min<unsigned>(8, std::max<unsigned>(1, hw / 2));
 		if(const char* e = getenv("CFB_READ_THREADS")) read_threads = std::max(1, atoi(e));
 	}
 	~TextPipe() { for(int m = 0; m < 2; m++) for(size_t i = 0; i < buf[m].size(); i++) cfb_host_free(buf[m][i]); }
 	bool init(bool paired) {
-		nslots = std::min(cfb_ctx_slots(ctx), 4); cap = 2 * o.text_block + 4096;     // 4 spans cover reader + 2 on the device + writer
-		for(int m = 0; m < (paired ? 2 : 1); m++) while((int)buf[m].size() < nslots) {
+		S = std::min(cfb_ctx_slots(ctxs[0]), 4); cap = 2 * o.text_block + 4096;
+		const size_t want = (size_t)S * ctxs.size();
+		for(int m = 0; m < (paired ? 2 : 1); m++) while(buf[m].size() < want) {
 			unsigned char* p = (unsigned char*)cfb_host_alloc(cap);
 			if(!p) return false;
 			buf[m].push_back(p);
 		}
 		return true;
 	}
-	struct Span { int slot; size_t bytes[2]; size_t rec; uint64_t start[2]; uint32_t hint; bool irregular; };
-	struct Rows { int slot; const char* tsv; uint64_t tsv_bytes; const uint64_t* multi; uint64_t n_multi; uint32_t stride; };
+	struct Span { int dev, slot; size_t bytes[2]; size_t rec; uint64_t start[2]; uint32_t hint; bool irregular; };
+	struct Rows { int dev, slot; const char* tsv; uint64_t tsv_bytes; const uint64_t* multi; uint64_t n_multi; uint32_t stride; };
 
-	// Runs one source.  Returns 0 when it was consumed completely, 1 when the record-level reader has to
+	// Runs one file (pair).  Returns 0 when it was consumed completely, 1 when the record-level reader has to
 	// continue from byte offsets off[0..1] after `done` records, -1 on error.
 	int run(const std::string& pa, const std::string* pb, uint64_t off[2], uint64_t& done) {
 		const bool paired = pb != NULL; const size_t L = o.fasta ? 2 : 4; const int nm = paired ? 2 : 1;
+		const int N = (int)ctxs.size();
 		off[0] = off[1] = 0; done = 0;
 		SpanFile f[2];
 		if(!f[0].open(pa) || (paired && !f[1].open(*pb))) { f[0].close(); f[1].close(); return 1; }   // not a regular file: the stream reader handles it (and reports errors)
@@ -720,20 +725,22 @@ struct TextPipe {
 		if(!init(paired)) { std::cerr << "Error: could not allocate pinned buffers" << std::endl; return -1; }
 		const double t_begin = now_s();
 		st.t_setup += t_begin - t_setup0;
-		Chan<int> free_slots; Chan<Span> spans; Chan<Rows> rows;
-		for(int i = 0; i < nslots; i++) free_slots.push(i);
+		std::vector<Chan<int> > free_slots(N); Chan<Span> spans; Chan<Rows> rows;
+		for(int d = 0; d < N; d++) for(int i = 0; i < S; i++) free_slots[d].push(i);
 		std::atomic<bool> stop(false);
 		double t_read = 0, t_write = 0;
 
 		std::thread reader([&] {
 			bool first = true;
-			for(;;) {
+			for(uint64_t k = 0;; k++) {
+				const int d = (int)(k % (uint64_t)N);
 				int s;
-				if(!free_slots.pop(s) || stop.load()) break;
+				if(!free_slots[d].pop(s) || stop.load()) break;
+				const int bi = d * S + s;
 				const double t0 = now_s();
-				Span sp; memset(&sp, 0, sizeof sp); sp.slot = s;
+				Span sp; memset(&sp, 0, sizeof sp); sp.dev = d; sp.slot = s;
 				size_t n[2] = {0, 0}, lines[2] = {0, 0};
-				for(int m = 0; m < nm; m++) n[m] = f[m].fill(buf[m][s], cap, o.text_block, &lines[m], read_threads);
+				for(int m = 0; m < nm; m++) n[m] = f[m].fill(buf[m][bi], cap, o.text_block, &lines[m], read_threads);
 				if(n[0] == 0 && (!paired || n[1] == 0)) { t_read += now_s() - t0; break; }      // input exhausted
 				size_t rec = lines[0] / L;
 				bool irregular = f[0].eof && lines[0] % L != 0;
@@ -741,7 +748,7 @@ struct TextPipe {
 				if(rec == 0) irregular = true;                       // a record longer than a span, or mates running out of step
 				sp.start[0] = f[0].span_start; sp.start[1] = paired ? f[1].span_start : 0; sp.irregular = irregular; sp.rec = rec;
 				if(!irregular) {
-					for(int m = 0; m < nm; m++) sp.bytes[m] = f[m].cut(buf[m][s], n[m], lines[m], rec * L);
+					for(int m = 0; m < nm; m++) sp.bytes[m] = f[m].cut(buf[m][bi], n[m], lines[m], rec * L);
 					// A FASTA record runs up to the next '>' (pat.cpp:806-826), so its last line inside the span need not be
 					// its end: unless the byte after the cut is '>' (or the input ends there), the tail record may continue in
 					// the next span and is carried over whole; the wrapped record then sits inside one span, where the strict
@@ -752,14 +759,14 @@ struct TextPipe {
 						if(open_tail) {
 							rec -= 1; sp.rec = rec;
 							if(rec == 0) { irregular = true; sp.irregular = true; }
-							else for(int m = 0; m < nm; m++) sp.bytes[m] = f[m].cut(buf[m][s], n[m], lines[m], rec * L);
+							else for(int m = 0; m < nm; m++) sp.bytes[m] = f[m].cut(buf[m][bi], n[m], lines[m], rec * L);
 						}
 					}
 				}
 				if(!irregular) {
 					if(first) {     // longest line in the head of the file sizes the first pass
 						first = false; size_t longest = 0, ls = 0; const size_t lim = std::min<size_t>(sp.bytes[0], 1u << 16);
-						for(size_t i = 0; i < lim; i++) if(buf[0][s][i] == '\n') { longest = std::max(longest, i - ls); ls = i + 1; }
+						for(size_t i = 0; i < lim; i++) if(buf[0][bi][i] == '\n') { longest = std::max(longest, i - ls); ls = i + 1; }
 						sp.hint = (uint32_t)std::min<size_t>(longest, 60000);
 					}
 				}
@@ -780,7 +787,7 @@ struct TextPipe {
 					multi[std::string((const char*)(rec + 1), (size_t)rec[0] * 8)] += 1;
 				}
 				t_write += now_s() - t0;
-				free_slots.push(r.slot);
+				free_slots[r.dev].push(r.slot);
 			}
 		});
 
@@ -792,13 +799,13 @@ struct TextPipe {
 			const Span sp = flight.front(); flight.pop_front();
 			cfb_text_result r;
 			const double t0 = now_s();
-			const int e = cfb_text_wait(ctx, sp.slot, fallback ? 1 : 0, &r);
+			const int e = cfb_text_wait(ctxs[sp.dev], sp.slot, fallback ? 1 : 0, &r);
 			t_wait += now_s() - t0;
-			if(e != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; rc = -1; fallback = true; stop.store(true); free_slots.push(sp.slot); return; }
-			if(fallback) { free_slots.push(sp.slot); return; }
-			if(r.irregular) { fallback = true; stop.store(true); off[0] = sp.start[0]; off[1] = sp.start[1]; st.fallbacks++; free_slots.push(sp.slot); return; }
+			if(e != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; rc = -1; fallback = true; stop.store(true); free_slots[sp.dev].push(sp.slot); return; }
+			if(fallback) { free_slots[sp.dev].push(sp.slot); return; }
+			if(r.irregular) { fallback = true; stop.store(true); off[0] = sp.start[0]; off[1] = sp.start[1]; st.fallbacks++; free_slots[sp.dev].push(sp.slot); return; }
 			done += r.n_units; st.spans++; st.units += r.n_units; st.bytes_out += r.tsv_bytes;
-			Rows w; w.slot = sp.slot; w.tsv = r.tsv; w.tsv_bytes = r.tsv_bytes; w.multi = r.multi; w.n_multi = r.n_multi; w.stride = r.multi_stride;
+			Rows w; w.dev = sp.dev; w.slot = sp.slot; w.tsv = r.tsv; w.tsv_bytes = r.tsv_bytes; w.multi = r.multi; w.n_multi = r.n_multi; w.stride = r.multi_stride;
 			rows.push(w);
 		};
 		for(;;) {
@@ -807,22 +814,24 @@ struct TextPipe {
 			if(sp.irregular) {
 				while(!flight.empty() && !fallback) collect_oldest();
 				if(!fallback) { fallback = true; off[0] = sp.start[0]; off[1] = sp.start[1]; st.fallbacks++; }
-				free_slots.push(sp.slot);
+				free_slots[sp.dev].push(sp.slot);
 				break;
 			}
 			if(sp.hint) to.maxlen_hint = sp.hint;
+			const int bi = sp.dev * S + sp.slot;
 			const double ts0 = now_s();
-			if(cfb_text_submit(ctx, sp.slot, buf[0][sp.slot], sp.bytes[0], paired ? buf[1][sp.slot] : NULL, sp.bytes[1], sp.rec, &to) != CFB_OK) {
-				std::cerr << "Error: " << cfb_last_error() << std::endl; rc = -1; fallback = true; stop.store(true); free_slots.push(sp.slot); break;
+			if(cfb_text_submit(ctxs[sp.dev], sp.slot, buf[0][bi], sp.bytes[0], paired ? buf[1][bi] : NULL, sp.bytes[1], sp.rec, &to) != CFB_OK) {
+				std::cerr << "Error: " << cfb_last_error() << std::endl; rc = -1; fallback = true; stop.store(true); free_slots[sp.dev].push(sp.slot); break;
 			}
 			st.t_submit += now_s() - ts0;
 			st.bytes_in += sp.bytes[0] + sp.bytes[1];
 			flight.push_back(sp);
-			// keep the device two spans deep; collect the oldest as soon as a third is queued
-			while((int)flight.size() > std::max(1, nslots - 2) && !fallback) collect_oldest();
+			// keep every device two spans deep; collect the oldest as soon as one more is queued
+			while((int)flight.size() > N * std::max(1, S - 2) && !fallback) collect_oldest();
 		}
 		while(!flight.empty()) collect_oldest();
-		stop.store(true); free_slots.close();
+		stop.store(true);
+		for(int d = 0; d < N; d++) free_slots[d].close();
 		{ Span sp; while(spans.pop(sp)) {} }      // reader may have queued spans after the failing one: they are re-read by the record reader
 		reader.join();
 		rows.close(); writer.join();
@@ -831,6 +840,31 @@ struct TextPipe {
 		if(rc < 0) return -1;
 		return fallback ? 1 : 0;
 	}
+};
+
+// One read list (-U a,b,c or the -1 / -2 lists) as the record-level reader sees it: the files one after another behind
+// one record counter, as BufferedFilePatternSource does (pat.h:786-811,883-904).
+struct ListIn {
+	std::vector<std::string> files; size_t next = 0; FileIn in; bool is_open = false, first = true;
+	bool open_next() {                  // BufferedFilePatternSource::open
+		while(next < files.size()) {
+			const std::string& p = files[next++];
+			if(in.open(p)) { is_open = true; first = true; return true; }
+			std::cerr << "Warning: Could not open read file \"" << p << "\" for reading; skipping..." << std::endl;
+		}
+		std::cerr << "Error: No input read files were valid" << std::endl;
+		throw 1;
+	}
+	// next record of the list; false when every file is exhausted
+	bool read(bool fasta, Rec& r, uint64_t& count, int trim5, int trim3) {
+		for(;;) {
+			if(!is_open) { if(next >= files.size()) return false; open_next(); }
+			const bool ok = fasta ? parse_fasta(in, r, count, first, trim5, trim3) : parse_fastq(in, r, count, first, trim5, trim3);
+			if(ok) return true;
+			in.close(); is_open = false;
+		}
+	}
+	void close() { if(is_open) in.close(); is_open = false; }
 };
 
 static void write_report(const HostIndex& h, const Options& o, Species& sp, int device) {   // centrifuge.cpp:3231-3319
@@ -914,6 +948,20 @@ static int parse_args(int argc, const char** argv, Options& o, bool& exit_now) {
 		else if(key == "5" || key == "trim5") o.trim5 = atoi(val.c_str());
 		else if(key == "3" || key == "trim3") o.trim3 = atoi(val.c_str());
 		else if(key == "device") o.device = atoi(val.c_str());
+		else if(key == "devices") {      // "0-7", "0,2,5", "all"
+			o.devices.clear();
+			if(val == "all") o.devices.push_back(-1);
+			else {
+				std::vector<std::string> parts = split(val, ',');
+				for(size_t k = 0; k < parts.size(); k++) {
+					const size_t dash = parts[k].find('-');
+					const int lo = atoi(parts[k].substr(0, dash).c_str()), hi = dash == std::string::npos ? lo : atoi(parts[k].substr(dash + 1).c_str());
+					if(lo < 0 || hi < lo || hi > 63) { std::cerr << "--devices arg must be a list of device numbers or ranges" << std::endl; return 1; }
+					for(int d = lo; d <= hi; d++) if(std::find(o.devices.begin(), o.devices.end(), d) == o.devices.end()) o.devices.push_back(d);
+				}
+				if(o.devices.empty()) { std::cerr << "--devices arg must be a list of device numbers or ranges" << std::endl; return 1; }
+			}
+		}
 		else if(key == "batch-units") o.batch_units = (size_t)strtoull(val.c_str(), NULL, 10);
 		else if(key == "text-block-mb") { const size_t mb = (size_t)strtoull(val.c_str(), NULL, 10); o.text_block = std::min<size_t>(std::max<size_t>(mb, 1), 1024) << 20; }
 		else if(key == "host-parse") o.host_parse = true;
@@ -932,6 +980,8 @@ static int parse_args(int argc, const char** argv, Options& o, bool& exit_now) {
 	if(o.mates1.size() != o.mates2.size()) { std::cerr << "Error: " << o.mates1.size() << " mate files/sequences were specified with -1, but " << o.mates2.size() << std::endl << "mate files/sequences were specified with -2.  The same number of mate files/" << std::endl << "sequences must be specified with -1 and -2." << std::endl; return 1; }
 	if(o.singles.empty() && o.mates1.empty()) { std::cerr << "No index, query, or output file specified!" << std::endl; return 1; }
 	if(o.batch_units < 1) o.batch_units = 1;
+	// -s together with -u: rdids are shifted up by the skipped reads (centrifuge.cpp:1628-1633, 32-bit arithmetic)
+	if(o.upto != std::numeric_limits<uint64_t>::max()) { const uint32_t u = (uint32_t)o.upto, sk = (uint32_t)o.skip; if((uint32_t)(u + sk) > u) o.upto = (uint32_t)(u + sk); }
 	if(const char* e = getenv("CFB_TEXT_BLOCK")) o.text_block = std::max<size_t>((size_t)strtoull(e, NULL, 10), 4096);   // bytes; tests use tiny spans
 	return 0;
 }
@@ -1060,6 +1110,16 @@ extern "C" int cfb_kreport(const char* index_base, const char* tsv_path, const c
 	return rc;
 }
 
+// everything a run owns, released on every way out (normal return, reader error -> throw 1, exception)
+struct RunState {
+	std::vector<cfb_index*> ix; std::vector<cfb_ctx*> ctx; FILE* fo = NULL;
+	~RunState() {
+		if(fo && fo != stdout) fclose(fo); else if(fo) fflush(stdout);
+		for(size_t i = 0; i < ctx.size(); i++) if(ctx[i]) cfb_ctx_destroy(ctx[i]);      // waits for batches still in flight
+		for(size_t i = 0; i < ix.size(); i++) if(ix[i]) cfb_index_free(ix[i]);
+	}
+};
+
 extern "C" int cfb_run(int argc, const char** argv) {
 	init_tables();
 	Options o; bool exit_now = false;
@@ -1067,24 +1127,40 @@ extern "C" int cfb_run(int argc, const char** argv) {
 		int rc = parse_args(argc, argv, o, exit_now);
 		if(rc || exit_now) return rc;
 		const auto t_start = std::chrono::steady_clock::now();
-		cfb_index* ix = NULL;
+		RunState rs;
+		// ---- devices: one replica of the index and one context per GPU
+		std::vector<int> devs = o.devices;
+		if(devs.size() == 1 && devs[0] == -1) { devs.clear(); int n = cfb_device_count(); for(int d = 0; d < n; d++) devs.push_back(d); if(devs.empty()) { std::cerr << "Error: no CUDA device (this build has no CPU fallback)" << std::endl; return 1; } }
+		if(devs.empty()) devs.push_back(o.device);
+		const int N = (int)devs.size();
 		// File-to-file runs are bounded by the file system (tens of M reads/s), far below what the plain kernels
 		// deliver (~180 M reads/s), so the tables that buy the last factor of two on the device (resolve table, walk8:
 		// ~0.75 s per Gbp to build) would only delay the first read.  CFB_FULL_TABLES=1 builds them anyway.
 		const uint32_t load_flags = getenv("CFB_FULL_TABLES") ? 0u : (CFB_LOAD_NO_RESOLVE_TABLE | CFB_LOAD_NO_WALK8);
-		if(cfb_index_load_ex(o.index.c_str(), o.device, load_flags, &ix) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; return 1; }
-		cfb_ctx* ctx = NULL;
-		if(cfb_ctx_create(ix, &o.prm, &ctx) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; cfb_index_free(ix); return 1; }
-		const HostIndex& h = *cfb_index_host(ix);
+		rs.ix.assign(N, (cfb_index*)NULL); rs.ctx.assign(N, (cfb_ctx*)NULL);
+		{
+			std::vector<std::string> errs(N); std::vector<std::thread> th;
+			auto load_one = [&](int i) {
+				if(cfb_index_load_ex(o.index.c_str(), devs[i], load_flags, &rs.ix[i]) != CFB_OK) { errs[i] = cfb_last_error(); return; }
+				if(cfb_ctx_create(rs.ix[i], &o.prm, &rs.ctx[i]) != CFB_OK) errs[i] = cfb_last_error();
+			};
+			for(int i = 1; i < N; i++) th.emplace_back(load_one, i);
+			load_one(0);
+			for(size_t i = 0; i < th.size(); i++) th[i].join();
+			for(int i = 0; i < N; i++) if(!errs[i].empty()) { std::cerr << "Error: " << errs[i] << std::endl; return 1; }
+		}
+		if(N > 1 && cfb_comm_init_all(rs.ctx.data(), N) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; return 1; }
+		cfb_ctx* ctx = rs.ctx[0];               // the record-level reader works on the first device
+		const HostIndex& h = *cfb_index_host(rs.ix[0]);
 		const auto t_loaded = std::chrono::steady_clock::now();
-		FILE* fo = o.out == "-" ? stdout : fopen(o.out.c_str(), "wb");
+		FILE* fo = rs.fo = o.out == "-" ? stdout : fopen(o.out.c_str(), "wb");
 		if(!fo) { std::cerr << "Error: could not open output file " << o.out << std::endl; return 1; }
 		fputs("readID\tseqID\ttaxID\tscore\t2ndBestScore\thitLength\tqueryLength\tnumMatches\n", fo);
 		Species sp; Formatter fmt(h, o, sp); KReport kr(h, o);
 		const int nslots = std::min(cfb_ctx_slots(ctx), 4);
 		std::vector<HostBatch> hb(nslots);
 		std::vector<bool> busy(nslots, false);
-		int cur = 0; uint64_t rdid = 0;
+		int cur = 0;
 		bool failed = false;
 		auto drain = [&](int s) -> bool {
 			cfb_result res;
@@ -1106,60 +1182,67 @@ extern "C" int cfb_run(int argc, const char** argv) {
 			busy[s] = true;
 			return true;
 		};
-		// all files in the reference's order: paired sources first? No: PairedDualPatternSource walks
-		// srca_ in the order {mates1..., singles...} (pat.cpp:330-420: m12, m1/m2, then singles)
-		struct Src { std::string a, b; bool paired; };
+		// The reference builds ONE pattern source per read list (all -1 files with all -2 files, then all -U files;
+		// pat.cpp:330-420): the record counter that names unnamed reads runs on across the files of a list, and mates
+		// keep pairing across file boundaries when the two lists are cut differently.
+		struct Src { std::vector<std::string> a, b; bool paired; };
 		std::vector<Src> srcs;
-		for(size_t i = 0; i < o.mates1.size(); i++) { Src s; s.a = o.mates1[i]; s.b = o.mates2[i]; s.paired = true; srcs.push_back(s); }
-		for(size_t i = 0; i < o.singles.size(); i++) { Src s; s.a = o.singles[i]; s.paired = false; srcs.push_back(s); }
+		if(!o.mates1.empty()) { Src s; s.a = o.mates1; s.b = o.mates2; s.paired = true; srcs.push_back(s); }
+		if(!o.singles.empty()) { Src s; s.a = o.singles; s.paired = false; srcs.push_back(s); }
 		bool stop = false;
 		MultiObs multi; TextStats tstats; uint64_t host_units = 0;
-		TextPipe pipe(ctx, o, fo, multi, tstats);
+		TextPipe pipe(rs.ctx, o, fo, multi, tstats);
 		if(kr.enabled()) pipe.kr = &kr;
 		const bool text_ok = !o.host_parse && !getenv("CFB_HOST_PARSE") && o.prm.khits <= 32 && o.skip == 0 && o.upto == std::numeric_limits<uint64_t>::max();
 		for(size_t si = 0; si < srcs.size() && !failed && !stop; si++) {
-			uint64_t off[2] = {0, 0}, done = 0;
-			if(text_ok && srcs[si].a != "-" && srcs[si].b != "-") {
-				const int r = pipe.run(srcs[si].a, srcs[si].paired ? &srcs[si].b : NULL, off, done);
+			const Src& src = srcs[si];
+			uint64_t off[2] = {0, 0}, cntA = 0, cntB = 0;      // cnt: records of this list read so far (PatternSource::readCnt_)
+			size_t fi = 0;
+			// whole files go through the text operator while they stay regular and the mate files stay in step
+			while(text_ok && fi < src.a.size() && src.a[fi] != "-" && !(src.paired && src.b[fi] == "-")) {
+				uint64_t done = 0;
+				const int r = pipe.run(src.a[fi], src.paired ? &src.b[fi] : NULL, off, done);
 				if(r < 0) { failed = true; break; }
-				rdid += done;
-				if(r == 0) continue;
+				cntA += done; cntB += done;
+				if(r != 0) break;                  // the record-level reader continues inside file fi, at off[]
+				off[0] = off[1] = 0; fi++;
 			}
-			FileIn fa, fb;
-			if(!fa.open(srcs[si].a)) { std::cerr << "Warning: Could not open read file \"" << srcs[si].a << "\" for reading; skipping..." << std::endl; continue; }
-			if(srcs[si].paired && !fb.open(srcs[si].b)) { std::cerr << "Warning: Could not open read file \"" << srcs[si].b << "\" for reading; skipping..." << std::endl; continue; }
-			bool firstA = true, firstB = true; uint64_t cntA = done, cntB = done;
+			if(failed || fi >= src.a.size()) continue;
+			ListIn la, lb;
+			la.files.assign(src.a.begin() + fi, src.a.end());
+			if(src.paired) lb.files.assign(src.b.begin() + fi, src.b.end());
 			// continue after the spans the text operator consumed: same parser state as if it had read them itself
-			auto resume = [&](FileIn& f, uint64_t at, bool& first) {
+			auto resume = [&](ListIn& l, uint64_t at) {
 				if(at == 0) return;
-				f.seek(at); first = false;
+				l.open_next(); l.in.seek(at); l.first = false;
+				FileIn& f = l.in;
 				if(!o.fasta) { while(f.peek() == '\n' || f.peek() == '\r') f.get(); f.get(); }   // the '@' that ends the previous record's parse
 				else { while(f.peek() >= 0 && f.peek() != '>') f.get(); }   // the previous record's sequence loop runs up to the next '>' (blank lines at a span start belong to it)
 			};
-			resume(fa, off[0], firstA);
-			if(srcs[si].paired) resume(fb, off[1], firstB);
+			resume(la, off[0]);
+			if(src.paired) resume(lb, off[1]);
 			Rec ra, rb;
-			hb[cur].clear(srcs[si].paired);
+			hb[cur].clear(src.paired);
 			for(;;) {
-				const bool okA = o.fasta ? parse_fasta(fa, ra, cntA, firstA, o.trim5, o.trim3) : parse_fastq(fa, ra, cntA, firstA, o.trim5, o.trim3);
+				const uint64_t id = cntA;          // rdid of this read: the list's own record counter (pat.h:603-611)
+				const bool okA = la.read(o.fasta, ra, cntA, o.trim5, o.trim3);
 				bool okB = true;
-				if(srcs[si].paired) okB = o.fasta ? parse_fasta(fb, rb, cntB, firstB, o.trim5, o.trim3) : parse_fastq(fb, rb, cntB, firstB, o.trim5, o.trim3);
-				if(!okA && srcs[si].paired && okB) { std::cerr << "Error, fewer reads in file specified with -1 than in file specified with -2" << std::endl; throw 1; }
+				if(src.paired) okB = lb.read(o.fasta, rb, cntB, o.trim5, o.trim3);
+				if(!okA && src.paired && okB) { std::cerr << "Error, fewer reads in file specified with -1 than in file specified with -2" << std::endl; throw 1; }
 				if(!okA) break;
 				if(!okB) { std::cerr << "Error, fewer reads in file specified with -2 than in file specified with -1" << std::endl; throw 1; }
 				// empty reads are kept: the reference reports them as length-filtered "unclassified" rows
-				const uint64_t id = rdid++;
 				if(id >= o.upto) { stop = true; break; }
 				if(id < o.skip) continue;
-				hb[cur].add(ra, srcs[si].paired ? &rb : NULL, o.seed); host_units++;
+				hb[cur].add(ra, src.paired ? &rb : NULL, o.seed); host_units++;
 				if(hb[cur].n >= o.batch_units) {
 					if(!flush(cur)) { failed = true; break; }
 					const int nxt = (cur + 1) % nslots;
 					if(busy[nxt] && !drain(nxt)) { failed = true; break; }
-					cur = nxt; hb[cur].clear(srcs[si].paired);
+					cur = nxt; hb[cur].clear(src.paired);
 				}
 			}
-			fa.close(); fb.close();
+			la.close(); lb.close();
 			if(failed) break;
 			// finish this source: submit the partial batch, then drain everything in submission order
 			if(!flush(cur)) { failed = true; break; }
@@ -1167,15 +1250,18 @@ extern "C" int cfb_run(int argc, const char** argv) {
 			hb[cur].clear(false);
 		}
 		if(!failed && tstats.units) {       // fold the device-side counters into the host maps
+			// several devices: one NCCL all-reduce (sum, u64) of the per-taxon counters over the replicas' contexts
+			const int global = N > 1 ? 1 : 0;
+			if(N > 1 && cfb_counts_allreduce(rs.ctx.data(), N, NULL, 0) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; failed = true; }
 			uint64_t n = 0;
-			if(cfb_text_species(ctx, NULL, NULL, NULL, NULL, 0, &n) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; failed = true; }
+			if(!failed && cfb_counts_read(ctx, global, NULL, NULL, NULL, NULL, 0, &n) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; failed = true; }
 			std::vector<uint64_t> tx(n), nr(n), nu(n), no(n);
-			if(!failed && n && cfb_text_species(ctx, tx.data(), nr.data(), nu.data(), no.data(), n, &n) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; failed = true; }
+			if(!failed && n && cfb_counts_read(ctx, global, tx.data(), nr.data(), nu.data(), no.data(), n, &n) != CFB_OK) { std::cerr << "Error: " << cfb_last_error() << std::endl; failed = true; }
 			for(uint64_t i = 0; i < n && !failed; i++) {
 				Counts& c = sp.counts[tx[i]]; c.n_reads += nr[i]; c.n_unique += nu[i];
 				if(no[i]) sp.observed[std::vector<uint64_t>(1, tx[i])] += no[i];
 			}
-			for(MultiObs::const_iterator it = multi.begin(); it != multi.end(); ++it) {
+			for(MultiObs::const_iterator it = multi.begin(); it != multi.end(); ++it) {      // sparse tie sets: merged on the host, as SpeciesMetrics::merge does
 				std::vector<uint64_t> ids(it->first.size() / 8);
 				memcpy(ids.data(), it->first.data(), ids.size() * 8);
 				sp.observed[ids] += it->second;
@@ -1187,11 +1273,12 @@ extern "C" int cfb_run(int argc, const char** argv) {
 			std::cerr << "[cfb] text operator: " << tstats.units << " units in " << tstats.spans << " spans (" << tstats.bytes_in << " bytes in, " << tstats.bytes_out
 			          << " bytes out, " << tstats.fallbacks << " fallbacks); record-level reader: " << host_units << " units" << std::endl;
 			std::cerr << "[cfb] text pipeline " << tstats.t_total << " s: reader busy " << tstats.t_read << " s, device wait " << tstats.t_gpu_wait << " s, writer busy " << tstats.t_write << " s, submit " << tstats.t_submit << " s, pinned setup " << tstats.t_setup << " s" << std::endl;
+			if(N > 1) std::cerr << "[cfb] " << N << " devices, per-taxon counters reduced with NCCL" << std::endl;
 		}
 		if(fo != stdout) fclose(fo); else fflush(stdout);
-		if(!failed && !o.report.empty()) write_report(h, o, sp, o.device);
+		rs.fo = NULL;
+		if(!failed && !o.report.empty()) write_report(h, o, sp, devs[0]);
 		if(!failed && kr.enabled()) kr.write();
-		cfb_ctx_destroy(ctx); cfb_index_free(ix);
 		return failed ? 1 : 0;
 	} catch(int e) {
 		return e ? e : 1;

@@ -76,6 +76,9 @@ static const uint64_t kRowMask = (1ull << 40) - 1ull, kRowStart = 1ull << 63, kR
 
 struct Counters {   // algorithmic-operation counters (SURVEY.md section 8d definition)
 	unsigned long long units, partial_searches, ftab_probes, sides_search, walk_steps, rows_resolved, lf_steps, ext_searches;
+	// the product's own load requests (count mode 2: every derived table live, one entry per lane-level gather):
+	// rank16 entries (16 B), 10-mer table entries (16 B), K-mer table entries (16 B), walk8 entries (8 B)
+	unsigned long long req_rank16, req_ftab2, req_ftabk, req_walk8;
 };
 
 CFB_HD int popc64(uint64_t x) {

@@ -245,8 +245,13 @@ struct FmtArgs {
 	uint32_t* row_bytes; const uint64_t* txt_off; uint8_t* sel; uint8_t* num; uint32_t* sec;
 	char* out; uint64_t out_cap;
 	unsigned long long* sp; unsigned long long* multi; uint32_t multi_stride; uint64_t multi_cap;
-	unsigned long long* tscal;
+	unsigned long long* tscal; uint32_t maxlen_hint;
 };
+// A span the tokeniser rejected (or that needs a wider length class) has no valid name / id / flag arrays: the
+// formatter must not touch them.  The bits tested here are final before the formatter starts.
+__device__ __forceinline__ bool span_rejected(const FmtArgs& a) {
+	return (*(volatile unsigned long long*)a.tscal & (TX_IRREGULAR | TX_LINECOUNT)) != 0 || *(volatile unsigned long long*)(a.tscal + 1) > a.maxlen_hint;
+}
 
 __device__ __forceinline__ uint32_t dec_digits(uint64_t v) { uint32_t n = 1; while(v >= 10) { v /= 10; n++; } return n; }
 __device__ __forceinline__ char* put_dec(char* p, uint64_t v) {
@@ -274,6 +279,7 @@ struct Lcg32 { uint32_t last; __device__ __forceinline__ uint32_t next() { last 
 __global__ void __launch_bounds__(128) k_fmt_plan(const FmtArgs a) {
 	const uint32_t u = blockIdx.x * 128 + threadIdx.x;
 	const bool live = u < a.n_units;
+	if(span_rejected(a)) { if(live) a.row_bytes[u] = 0; return; }
 	uint32_t r0 = 0, r1 = 0;
 	if(live) { r0 = a.rec_off[u]; r1 = a.rec_off[u + 1]; }
 	const bool uncl = r1 == r0;
@@ -361,6 +367,7 @@ __global__ void __launch_bounds__(128) k_fmt_plan(const FmtArgs a) {
 static const int kFmtShBytes = 16 * 1024;      // 128 units x ~60-byte rows fit with room to spare; 12 CTAs per SM stay resident
 __global__ void __launch_bounds__(128, 12) k_fmt_write(const FmtArgs a) {
 	__shared__ char sh[kFmtShBytes];
+	if(span_rejected(a)) return;
 	const uint32_t u0 = blockIdx.x * 128, u1 = min(u0 + 128u, a.n_units);
 	const uint64_t base = a.txt_off[u0], end = a.txt_off[u1], span = end - base;
 	if(a.txt_off[a.n_units] > a.out_cap) return;             // host grows the buffer and relaunches
@@ -420,15 +427,13 @@ struct TextSlot {
 };
 struct TextCtx {
 	bool ready = false;
-	DBuf<uint64_t> nd_taxid; DBuf<uint8_t> nd_info; DBuf<uint64_t> sp_taxid; DBuf<uint32_t> sn_off; DBuf<char> sn_blob; DBuf<uint8_t> rk_off; DBuf<char> rk_blob;
-	DBuf<unsigned long long> sp_total;
-	std::vector<uint64_t> h_sp_taxid;
-	FmtTables tb;
+	DBuf<uint64_t> nd_taxid; DBuf<uint8_t> nd_info; DBuf<uint32_t> sn_off; DBuf<char> sn_blob; DBuf<uint8_t> rk_off; DBuf<char> rk_blob;
+	FmtTables tb;       // the per-taxon counter space (sp_taxid) and its totals live in the context (CountsCtx)
 	uint32_t maxlen_hint = 128;
 	double tsv_ratio = 64.0, multi_ratio = 0.05;     // bytes / tie sets per unit seen so far (size the speculative D2H)
 	TextSlot slots[kSlots - 1];
 	void release() {
-		nd_taxid.release(); nd_info.release(); sp_taxid.release(); sn_off.release(); sn_blob.release(); rk_off.release(); rk_blob.release(); sp_total.release();
+		nd_taxid.release(); nd_info.release(); sn_off.release(); sn_blob.release(); rk_off.release(); rk_blob.release();
 		for(int i = 0; i < kSlots - 1; i++) slots[i].release();
 	}
 };
@@ -442,8 +447,7 @@ static int text_init(cfb_ctx* c) {
 	const HostIndex& h = c->ix->h;
 	std::vector<uint64_t> nt(h.nodes.size()); std::vector<uint8_t> ni(h.nodes.size());
 	for(size_t i = 0; i < h.nodes.size(); i++) { nt[i] = h.nodes[i].taxid; ni[i] = (uint8_t)((h.nodes[i].rank & 0x7f) | (h.nodes[i].leaf ? 0x80 : 0)); }
-	std::set<uint64_t> sp(nt.begin(), nt.end()); sp.insert(0); sp.insert(1); sp.insert(h.seq_taxid.begin(), h.seq_taxid.end());
-	t.h_sp_taxid.assign(sp.begin(), sp.end());
+	{ int rc = counts_init(c); if(rc) return rc; }
 	std::vector<uint32_t> so(h.seq_name.size() + 1, 0); std::string blob;
 	for(size_t i = 0; i < h.seq_name.size(); i++) { so[i] = (uint32_t)blob.size(); blob += h.seq_name[i]; }
 	so[h.seq_name.size()] = (uint32_t)blob.size();
@@ -453,11 +457,10 @@ static int text_init(cfb_ctx* c) {
 	ro[RANK_MAX] = (uint8_t)rb.size(); rb += "unclassified"; ro[RANK_MAX + 1] = (uint8_t)rb.size();
 	if(rb.size() > 255) return fail(CFB_EINVAL, "rank string table overflow");
 	#define UP(buf, vec) do { CK(buf.ensure((vec).size() + 1)); if(!(vec).empty()) CK(cudaMemcpy(buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice)); } while(0)
-	UP(t.nd_taxid, nt); UP(t.nd_info, ni); UP(t.sp_taxid, t.h_sp_taxid); UP(t.sn_off, so); UP(t.sn_blob, blob); UP(t.rk_off, ro); UP(t.rk_blob, rb);
+	UP(t.nd_taxid, nt); UP(t.nd_info, ni); UP(t.sn_off, so); UP(t.sn_blob, blob); UP(t.rk_off, ro); UP(t.rk_blob, rb);
 	#undef UP
-	CK(t.sp_total.ensure(3 * t.h_sp_taxid.size())); CK(cudaMemset(t.sp_total.p, 0, 3 * t.h_sp_taxid.size() * 8));
 	t.tb.nd_taxid = t.nd_taxid.p; t.tb.nd_info = t.nd_info.p; t.tb.n_nodes = (uint32_t)nt.size();
-	t.tb.sp_taxid = t.sp_taxid.p; t.tb.n_sp = (uint32_t)t.h_sp_taxid.size();
+	t.tb.sp_taxid = c->cnt.d_taxid.p; t.tb.n_sp = c->cnt.n;
 	t.tb.sn_off = t.sn_off.p; t.tb.sn_blob = t.sn_blob.p; t.tb.n_seq = (uint32_t)h.seq_name.size();
 	t.tb.rk_off = t.rk_off.p; t.tb.rk_blob = t.rk_blob.p;
 	t.ready = true;
@@ -482,7 +485,7 @@ static int text_enqueue_format(cfb_ctx* c, Slot& s, TextSlot& t) {
 	fa.flags = s.bv.flags; fa.rec_off = s.rec_off32.p; fa.recs = s.dense.p; fa.n_units = (uint32_t)n; fa.n_mates = t.n_mates; fa.khits = c->prm.khits;
 	fa.row_bytes = t.row_bytes.p; fa.txt_off = t.txt_off.p; fa.sel = t.sel.p; fa.num = t.num.p; fa.sec = t.sec.p;
 	fa.out = t.d_tsv.p; fa.out_cap = t.d_tsv.cap; fa.sp = t.sp.p; fa.multi = t.multi.p; fa.multi_stride = stride; fa.multi_cap = n;
-	fa.tscal = t.tscal.p;
+	fa.tscal = t.tscal.p; fa.maxlen_hint = s.maxlen;
 	k_fmt_plan<<<ublocks, 128, 0, s.st>>>(fa);
 	k_scan_sums<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(t.row_bytes.p, n, s.bsum.p);
 	k_scan_top<<<1, 1024, 0, s.st>>>(s.bsum.p, scan_blocks, (uint64_t*)(t.tscal.p + 6));
@@ -582,7 +585,7 @@ extern "C" int cfb_text_submit(cfb_ctx* c, int slot, const void* text_a, uint64_
 	for(int m = 0; m < 2; m++) { s.bv.off[m] = m < nm ? s.d_off.p + m * (n + 1) : nullptr; s.bv.len[m] = m < nm ? s.d_len.p + m * n : nullptr; }
 	s.n_bases = bytes_a + t.bytes[1];
 	if(o->maxlen_hint) tc.maxlen_hint = std::max(tc.maxlen_hint, len_class(o->maxlen_hint));
-	s.maxlen = tc.maxlen_hint; s.want_host = false;
+	s.maxlen = tc.maxlen_hint; s.want_host = false; s.is_text = true;
 	rc = text_enqueue_all(c, s, t); if(rc) return rc;
 	s.pending = true; t.pending = true;
 	return CFB_OK;
@@ -629,7 +632,7 @@ extern "C" int cfb_text_wait(cfb_ctx* c, int slot, int discard, cfb_text_result*
 			CK(cudaMemcpyAsync(t.h_multi.p, t.multi.p, n_multi * out->multi_stride * 8, cudaMemcpyDeviceToHost, s.st));
 			more = true;
 		}
-		if(!discard) { const uint32_t nsp3 = 3 * tc.tb.n_sp; k_sp_commit<<<(nsp3 + 255) / 256, 256, 0, s.st>>>(t.sp.p, tc.sp_total.p, nsp3); c->launches++; }
+		if(!discard) { const uint32_t nsp3 = 3 * tc.tb.n_sp; k_sp_commit<<<(nsp3 + 255) / 256, 256, 0, s.st>>>(t.sp.p, c->cnt.total.p, nsp3); c->launches++; c->cnt.reduced = false; }
 		if(more) CK(cudaStreamSynchronize(s.st));
 		out->tsv = t.h_tsv.p; out->tsv_bytes = tsv; out->multi = (const uint64_t*)t.h_multi.p; out->n_multi = n_multi;
 		return CFB_OK;
@@ -638,19 +641,5 @@ extern "C" int cfb_text_wait(cfb_ctx* c, int slot, int discard, cfb_text_result*
 }
 
 extern "C" int cfb_text_species(cfb_ctx* c, uint64_t* taxid, uint64_t* n_reads, uint64_t* n_unique, uint64_t* n_obs1, uint64_t cap, uint64_t* n) {
-	if(!c || !n) return fail(CFB_EINVAL, "null argument");
-	*n = 0;
-	if(!c->text || !c->text->ready) return CFB_OK;
-	CK(cudaSetDevice(c->ix->device));
-	TextCtx& tc = *c->text; const size_t nsp = tc.h_sp_taxid.size();
-	std::vector<unsigned long long> h(3 * nsp);
-	CK(cudaDeviceSynchronize());
-	CK(cudaMemcpy(h.data(), tc.sp_total.p, 3 * nsp * 8, cudaMemcpyDeviceToHost));
-	uint64_t k = 0;
-	for(size_t i = 0; i < nsp; i++) if(h[i]) {
-		if(k < cap && taxid && n_reads && n_unique && n_obs1) { taxid[k] = tc.h_sp_taxid[i]; n_reads[k] = h[i]; n_unique[k] = h[nsp + i]; n_obs1[k] = h[2 * nsp + i]; }
-		k++;
-	}
-	*n = k;
-	return CFB_OK;
+	return cfb_counts_read(c, 0, taxid, n_reads, n_unique, n_obs1, cap, n);
 }

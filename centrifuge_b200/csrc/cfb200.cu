@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <thread>
 #include <fcntl.h>
 #include <unistd.h>
@@ -644,20 +645,23 @@ template <int RW> struct ReadRegs {
 	}
 };
 
-template <bool COUNT, int RW>
+// COUNT: 0 = product; 1 = the reference's operation counters (jump tables off, so that the operation sequence is the
+// reference's); 2 = the product's own load requests with every table live (what the roofline of *this* kernel is made of)
+template <int COUNT, int RW>
 __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a) {      // 9 CTAs per SM at 52 registers; forcing 10 (48 registers) measured no faster: the DRAM gather rate is the limit
 	const ulonglong2* r16 = reinterpret_cast<const ulonglong2*>(a.v.rank16);
 	const ulonglong2* ftab2 = reinterpret_cast<const ulonglong2*>(a.v.ftab2);
 	const ulonglong2* ftabk = reinterpret_cast<const ulonglong2*>(a.v.ftabk);
-	const uint32_t fk = (COUNT || !a.v.ftabk) ? 0u : (uint32_t)a.v.ftabk_chars;   // counters follow the reference's op sequence
+	const uint32_t fk = (COUNT == 1 || !a.v.ftabk) ? 0u : (uint32_t)a.v.ftabk_chars;   // counters follow the reference's op sequence
 	const uint32_t fc = (uint32_t)a.v.ftab_chars;
-	const unsigned long long* w8 = COUNT ? nullptr : reinterpret_cast<const unsigned long long*>(a.v.walk8);
+	const unsigned long long* w8 = COUNT == 1 ? nullptr : reinterpret_cast<const unsigned long long*>(a.v.walk8);
 	ReadRegs<RW> rd;
 	uint64_t top = 0, bot = 0, fi = 0;
 	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0, slow_until = 0;
 	bool nolong = true;      // no hit of this strand reaches min_hitlen (kListNoLong tells the per-unit kernels)
 	int mode = M_NEED;
 	unsigned long long c_ps = 0, c_ft = 0, c_sides = 0, c_lf = 0;
+	unsigned long long q_r16 = 0, q_f2 = 0, q_fk = 0, q_w8 = 0;
 	WarpPool pool; pool.base = pool.end = 0;
 	bool more = true;      // warp-uniform: the global task counter is not exhausted yet
 
@@ -677,7 +681,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 	// partialSearch prologue (hi_aligner.h:939-982) at `cur`: ends in M_FTAB (fi set) or M_NEED
 	auto start_search = [&]() {
 		for(;;) {
-			if(COUNT) c_ps++;
+			if(COUNT == 1) c_ps++;
 			offset = cur;
 			if(rlen - cur < fc) { emit(kOff, kOff, offset, rlen - offset); a.nhits[tid] = nh | (nolong ? kListNoLong : 0u); mode = M_NEED; return; }
 			uint64_t win; uint32_t nwin; rd.window(cur, win, nwin);
@@ -729,8 +733,8 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 		ulonglong2 e = make_ulonglong2(0, 0), tq = e, bq = e;
 		const bool lf = mode == M_LF;
 		bool range = false, jump = false;
-		if(mode == M_FTAB) e = __ldg(ftab2 + fi);                           // (top, bot) of the 10-mer: one request
-		else if(mode == M_FTABK) e = __ldg(ftabk + fi);                     // (top, bot) of the K-mer
+		if(mode == M_FTAB) { e = __ldg(ftab2 + fi); if(COUNT == 2) q_f2++; }                           // (top, bot) of the 10-mer: one request
+		else if(mode == M_FTABK) { e = __ldg(ftabk + fi); if(COUNT == 2) q_fk++; }                     // (top, bot) of the K-mer
 		else if(lf) {
 			c = rd.base(dep);
 			if(c <= 3) {
@@ -738,13 +742,13 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 				if(w8 && (bot - top) <= (uint64_t)kJumpRows && dep >= slow_until && rlen - dep >= 8) {
 					// eight steps in one gather: a single row, or a narrow range whose rows (consecutive walk8 entries, one
 					// or two sectors) all continue with the read's next eight bases -- LF keeps such rows adjacent
-					jump = true; e.x = __ldg(w8 + top); e.y = 0;
+					jump = true; e.x = __ldg(w8 + top); e.y = 0; if(COUNT == 2) q_w8++;
 					#pragma unroll
 					for(int i = 1; i < kJumpRows; i++) if(top + i < bot) { const unsigned long long o = __ldg(w8 + top + i); e.y |= (o ^ e.x) >> 40; }   // bases + count must equal entry 0's
 				} else {
 					tq = __ldg(r16 + (top >> 6) * 4 + c);                   // (occ, bits): one request per rank query
-					bq = tq;
-					if(range && (bot >> 6) != (top >> 6)) bq = __ldg(r16 + (bot >> 6) * 4 + c);
+					bq = tq; if(COUNT == 2) q_r16++;
+					if(range && (bot >> 6) != (top >> 6)) { bq = __ldg(r16 + (bot >> 6) * 4 + c); if(COUNT == 2) q_r16++; }
 				}
 			}
 		}
@@ -755,7 +759,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 				if(dep < rlen) mode = M_LF; else hit_and_restart();
 			} else { fi &= (1ull << (2 * fc)) - 1ull; mode = M_FTAB; }   // died between base fc and K: replay from the 10-mer
 		} else if(mode == M_FTAB) {
-			if(COUNT) c_ft++;
+			if(COUNT == 1) c_ft++;
 			top = e.x; bot = e.y;
 			dep = cur + fc;
 			if(bot <= top) {                              // hi_aligner.h:971-982
@@ -784,7 +788,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 					b = t + 1;
 				}
 				if(b <= t) fail = true;
-				if(COUNT) {   // counters keep the reference's side geometry (384 rows per 128-byte side)
+				if(COUNT == 1) {   // counters keep the reference's side geometry (384 rows per 128-byte side)
 					uint64_t sT; uint32_t offT; row_locus(top, sT, offT);
 					const bool same_side = !range || (bot - top) < (uint64_t)(384 - offT);
 					c_lf += range ? 2 : 1; c_sides += same_side ? 1 : 2;
@@ -794,20 +798,23 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 			else { top = t; bot = b; dep++; if(dep >= rlen) hit_and_restart(); }
 		}
 	}
-	if(COUNT && a.ctr) {
+	if(COUNT == 1 && a.ctr) {
 		atomicAdd(&a.ctr->partial_searches, c_ps); atomicAdd(&a.ctr->ftab_probes, c_ft);
 		atomicAdd(&a.ctr->sides_search, c_sides); atomicAdd(&a.ctr->lf_steps, c_lf);
+	}
+	if(COUNT == 2 && a.ctr) {
+		atomicAdd(&a.ctr->req_rank16, q_r16); atomicAdd(&a.ctr->req_ftab2, q_f2); atomicAdd(&a.ctr->req_ftabk, q_fk); atomicAdd(&a.ctr->req_walk8, q_w8);
 	}
 }
 
 typedef void (*SearchKernel)(const SearchArgs);
 // g: lanes per walk (2,4,8 = cooperative kernels on the sides; 16 = their G=1 instantiation);
 // 1 / 100 = thread-per-walk kernels with the read in 4 / 10 register words
-static SearchKernel search_kernel(int g, bool count) {
+static SearchKernel search_kernel(int g, int count) {
 	switch(g) {
-		case 1: return count ? k_search_t<true, 4> : k_search_t<false, 4>;      // reads up to 128 bases
-		case 101: return count ? k_search_t<true, 5> : k_search_t<false, 5>;    // reads up to 160 bases (2 x 150 bp runs)
-		case 100: return count ? k_search_t<true, 10> : k_search_t<false, 10>;  // reads up to 320 bases
+		case 1: return count == 2 ? k_search_t<2, 4> : (count ? k_search_t<1, 4> : k_search_t<0, 4>);      // reads up to 128 bases
+		case 101: return count == 2 ? k_search_t<2, 5> : (count ? k_search_t<1, 5> : k_search_t<0, 5>);    // reads up to 160 bases (2 x 150 bp runs)
+		case 100: return count == 2 ? k_search_t<2, 10> : (count ? k_search_t<1, 10> : k_search_t<0, 10>);  // reads up to 320 bases
 		case 16: return count ? k_search<true, 1> : k_search<false, 1>;   // generic template at G = 1 (A/B only)
 		case 2: return count ? k_search<true, 2> : k_search<false, 2>;
 		case 4: return count ? k_search<true, 4> : k_search<false, 4>;
@@ -1530,6 +1537,8 @@ struct Slot {
 	DBuf<unsigned long long> scal;    // [0] search task ctr (u32 used), [1] resolve ctr, [2] overflow, [3] total rows, [4] total recs
 	HBuf<unsigned long long> h_scal;
 	HBuf<OutRec> h_recs; HBuf<uint32_t> h_rec_off;
+	DBuf<unsigned long long> cnt;     // this batch's per-taxon counters (record path), added to the context's totals at wait time
+	bool folded = false, is_text = false;
 	// batch bookkeeping
 	BatchView bv; uint64_t n_units = 0, n_bases = 0; uint32_t maxlen = 0, cap = 0; uint64_t rows_cap = 0, dense_cap = 0;
 	bool pending = false, reran = false;
@@ -1537,7 +1546,7 @@ struct Slot {
 	void release() {
 		h_bases.release(); h_off.release(); h_len.release(); h_flags.release(); d_bases.release(); d_off.release(); d_len.release(); d_flags.release();
 		pk.release(); nm.release(); hits.release(); nhits.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
-		sparse.release(); nout.release(); out_off.release(); dense.release(); rec_off32.release(); scal.release(); h_scal.release(); h_recs.release(); h_rec_off.release();
+		sparse.release(); nout.release(); out_off.release(); dense.release(); rec_off32.release(); scal.release(); h_scal.release(); h_recs.release(); h_rec_off.release(); cnt.release();
 		for(int i = 0; i < 6; i++) if(ev[i]) cudaEventDestroy(ev[i]);
 		if(st) cudaStreamDestroy(st);
 	}
@@ -1546,19 +1555,34 @@ struct Slot {
 struct cfb_dbatch { int slot; };
 struct TextCtx;                       // cf_text.cuh
 static void text_release(cfb_ctx*);
+static void comm_release(cfb_ctx*);   // cf_multi.cuh
+
+// Per-taxon counters of a context, on the device (SpeciesMetrics::addSpeciesCounts, aln_sink.h:142-172): for every taxid
+// the report can mention -- tree nodes, sequence taxids, 0 and 1 -- {numReads, numUniqueReads, reads whose single
+// best row reached the maximum score}.  Both the text operator (k_fmt_plan) and the record-level path (k_fold_counts,
+// when cfb_ctx_count_records is on) add to `total` when a batch is collected; cfb_counts_allreduce sums `total` over the
+// communicator's ranks into `global` (NCCL, ncclUint64, ncclSum).
+struct CountsCtx {
+	bool ready = false;
+	std::vector<uint64_t> h_taxid; DBuf<uint64_t> d_taxid; uint32_t n = 0;
+	DBuf<unsigned long long> total, global; bool reduced = false;
+	void release() { d_taxid.release(); total.release(); global.release(); }
+};
 
 struct cfb_ctx {
 	const cfb_index* ix = nullptr;
 	IndexView view; Params prm;
 	DBuf<uint8_t> d_excl; DBuf<uint64_t> d_host;
 	Slot slots[kSlots];
-	Counters* d_ctr = nullptr; bool count = false;
+	Counters* d_ctr = nullptr; int count = 0;        // CFB_COUNT: 1 = reference operation counters, 2 = the product's own load requests
 	uint64_t launches = 0;
 	int search_blocks = 0, resolve_blocks = 0, group = 1; int resolve_mode = 2;   // 0 = 8-lane sides, 1 = thread/blocks, 2 = 4-lane rank16
 	cfb_dbatch resident; bool resident_used = false;
 	double rec_ratio = 2.0;       // records per unit seen so far (sizes the speculative D2H)
 	uint64_t rows_cap0 = 0;       // CFB_ROWS_CAP: initial row-buffer capacity (tests force the grow-and-re-run path with it)
 	TextCtx* text = nullptr;
+	CountsCtx cnt; bool fold_records = false;
+	void* comm = nullptr; int comm_rank = 0, comm_size = 1; cudaStream_t comm_st = nullptr;      // NCCL communicator (cf_multi.cuh)
 };
 
 // every tree node whose ancestor chain contains a listed id (Classifier ctor classifier.h:157-201)
@@ -1581,6 +1605,8 @@ extern "C" void cfb_ctx_destroy(cfb_ctx* c) {
 	if(!c) return;
 	if(c->ix && c->ix->device >= 0) cudaSetDevice(c->ix->device);
 	text_release(c);
+	comm_release(c);
+	c->cnt.release();
 	for(int i = 0; i < kSlots; i++) c->slots[i].release();
 	c->d_excl.release(); c->d_host.release();
 	if(c->d_ctr) cudaFree(c->d_ctr);
@@ -1651,13 +1677,89 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
 	{ const char* rc0 = getenv("CFB_ROWS_CAP"); if(rc0) c->rows_cap0 = strtoull(rc0, NULL, 10); }
 	const char* cnt = getenv("CFB_COUNT");
-	c->count = cnt && cnt[0] == '1';
+	c->count = cnt ? (cnt[0] == '1' ? 1 : (cnt[0] == '2' ? 2 : 0)) : 0;
 	#undef CKC
 	*out = c;
 	return CFB_OK;
 }
 extern "C" int cfb_ctx_slots(const cfb_ctx*) { return kSlots - 1; }   // last slot is reserved for resident batches
 extern "C" int cfb_ctx_kernel_launches(const cfb_ctx* c, uint64_t* n) { if(!c || !n) return CFB_EINVAL; *n = c->launches; return CFB_OK; }
+
+// ---------------------------------------------------------------------------------------
+// per-taxon counters of the record-level path
+// ---------------------------------------------------------------------------------------
+static int counts_init(cfb_ctx* c) {
+	CountsCtx& k = c->cnt;
+	if(k.ready) return CFB_OK;
+	const HostIndex& h = c->ix->h;
+	std::set<uint64_t> sp; sp.insert(0); sp.insert(1);
+	for(size_t i = 0; i < h.nodes.size(); i++) sp.insert(h.nodes[i].taxid);
+	sp.insert(h.seq_taxid.begin(), h.seq_taxid.end());
+	k.h_taxid.assign(sp.begin(), sp.end()); k.n = (uint32_t)k.h_taxid.size();
+	CK(k.d_taxid.ensure(k.n + 1)); CK(cudaMemcpy(k.d_taxid.p, k.h_taxid.data(), (size_t)k.n * 8, cudaMemcpyHostToDevice));
+	CK(k.total.ensure(3ull * k.n)); CK(cudaMemset(k.total.p, 0, 3ull * k.n * 8));
+	CK(k.global.ensure(3ull * k.n)); CK(cudaMemset(k.global.p, 0, 3ull * k.n * 8));
+	k.ready = true;
+	return CFB_OK;
+}
+
+struct FoldArgs {
+	const uint64_t* sp_taxid; uint32_t n_sp;
+	const uint32_t* rec_off; const OutRec* recs; uint32_t n_units; int32_t n_mates; uint32_t khits;
+	const uint32_t* len[2]; const uint8_t* flags;
+	unsigned long long* sp;        // 3 * n_sp: numReads | numUniqueReads | observed singletons
+};
+__device__ __forceinline__ int find_slot(const uint64_t* a, uint32_t n, uint64_t key) {
+	uint32_t lo = 0, hi = n;
+	while(lo < hi) { const uint32_t mid = (lo + hi) >> 1; if(a[mid] < key) lo = mid + 1; else hi = mid; }
+	return (lo < n && a[lo] == key) ? (int)lo : -1;
+}
+// thread per unit: what AlnSinkWrap::finishRead -> SpeciesMetrics::addSpeciesCounts accumulate for the unit's reported
+// assignments (aln_sink.h:142-172,1861-1927): the records with the best score, at most khits of them (hit-map order; a tie
+// of more than khits records is resolved by the per-read RNG in the reference and in the text operator -- it only arises
+// under --host-taxids).  A unit without records counts as taxid 0, as its "unclassified" row does.
+__global__ void __launch_bounds__(128) k_fold_counts(const FoldArgs a) {
+	const uint32_t u = blockIdx.x * 128 + threadIdx.x;
+	const bool live = u < a.n_units;
+	int first_slot = -1; uint32_t num = 1; bool qualifies = false;
+	if(live) {
+		const uint32_t r0 = a.rec_off[u], r1 = a.rec_off[u + 1];
+		if(r1 == r0) { first_slot = find_slot(a.sp_taxid, a.n_sp, 0); qualifies = true; }
+		else {
+			uint32_t best = 0, ties = 0;
+			for(uint32_t k = r0; k < r1; k++) { const uint32_t sc = a.recs[k].score; if(sc > best || k == r0) { best = sc; ties = 1; } else if(sc == best) ties++; }
+			num = ties < a.khits ? ties : a.khits;
+			const uint32_t fl = a.flags ? a.flags[u] : 3u;
+			int64_t max_score = 0;
+			if(fl & 1u) { const int64_t L = a.len[0][u]; max_score += L > 15 ? (L - 15) * (L - 15) : 0; }
+			if(a.n_mates == 2 && (fl & 2u)) { const int64_t L = a.len[1][u]; max_score += L > 15 ? (L - 15) * (L - 15) : 0; }
+			qualifies = (int64_t)best >= max_score;
+			uint32_t taken = 0;
+			for(uint32_t k = r0; k < r1 && taken < num; k++) {
+				if(a.recs[k].score != best) continue;
+				const int slot = find_slot(a.sp_taxid, a.n_sp, a.recs[k].taxid);
+				if(taken == 0) first_slot = slot; else if(slot >= 0) atomicAdd(a.sp + slot, 1ull);
+				taken++;
+			}
+		}
+	}
+	// first assignment of every unit: warp-aggregated (dominant taxa would serialise per-lane atomics)
+	const int key = live ? first_slot : -1;
+	const uint32_t peers = __match_any_sync(0xffffffffu, key);
+	if(key >= 0) {
+		const uint32_t uniq = __popc(__ballot_sync(peers, num == 1) & peers);
+		const uint32_t obs = __popc(__ballot_sync(peers, num == 1 && qualifies) & peers);
+		if((uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u)) {
+			atomicAdd(a.sp + key, (unsigned long long)__popc(peers));
+			if(uniq) atomicAdd(a.sp + a.n_sp + key, (unsigned long long)uniq);
+			if(obs) atomicAdd(a.sp + 2ull * a.n_sp + key, (unsigned long long)obs);
+		}
+	}
+}
+__global__ void k_cnt_commit(const unsigned long long* slot_sp, unsigned long long* total, uint32_t n) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n) { const unsigned long long v = slot_sp[i]; if(v) atomicAdd(total + i, v); }
+}
 
 // Validate + stage a batch into the slot's pinned buffers and enqueue H2D copies.
 static int stage_batch(cfb_ctx* c, Slot& s, const cfb_batch* b) {
@@ -1758,7 +1860,7 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	if(time_it) CK(cudaEventRecord(s.ev[2], s.st));
 	ResolveArgs ra; ra.v = c->view; ra.rows = s.rows.p; ra.ids = s.ids.p; ra.ids16 = nullptr; ra.total = (const uint64_t*)(s.scal.p + 3); ra.rows_cap = s.rows_cap;
 	ra.task_ctr = s.scal.p + 1; ra.chunk = c->resolve_mode >= 2 ? 64 : (c->resolve_mode == 1 ? 128 : 4); ra.ctr = ctr;
-	if(c->resolve_mode == 3 && !c->count) k_lookup<<<c->ix->sm_count * 8, 256, 0, s.st>>>(ra);
+	if(c->resolve_mode == 3 && c->count != 1) k_lookup<<<c->ix->sm_count * 8, 256, 0, s.st>>>(ra);
 	else if(c->resolve_mode >= 2) { if(c->count) k_resolve_c<true, false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve_c<false, false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
 	else if(c->resolve_mode == 1) { if(c->count) k_resolve_t<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve_t<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
 	else { if(c->count) k_resolve<true><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); else k_resolve<false><<<c->resolve_blocks, kSearchThreads, 0, s.st>>>(ra); }
@@ -1770,6 +1872,15 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	k_scan_apply<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.nout.p, n, s.bsum.p, (const uint64_t*)(s.scal.p + 4), s.out_off.p);
 	k_compact<<<(unsigned)((n + 1 + 127) / 128), 128, 0, s.st>>>((uint32_t)n, s.row_off.p, s.out_off.p, s.sparse.p, s.dense.p, s.rec_off32.p, s.dense_cap, (unsigned int*)(s.scal.p + 2));
 	c->launches += 4;
+	s.folded = false;
+	if(c->fold_records && !s.is_text) {      // this batch's per-taxon counters, on the device, from the records just written
+		const uint32_t nsp = c->cnt.n;
+		CK(s.cnt.ensure(3ull * nsp)); CK(cudaMemsetAsync(s.cnt.p, 0, 3ull * nsp * 8, s.st));
+		FoldArgs fa; fa.sp_taxid = c->cnt.d_taxid.p; fa.n_sp = nsp; fa.rec_off = s.rec_off32.p; fa.recs = s.dense.p; fa.n_units = (uint32_t)n; fa.n_mates = nm;
+		fa.khits = c->prm.khits; fa.len[0] = s.bv.len[0]; fa.len[1] = s.bv.len[1]; fa.flags = s.bv.flags; fa.sp = s.cnt.p;
+		k_fold_counts<<<ublocks, 128, 0, s.st>>>(fa); c->launches++;
+		s.folded = true;
+	}
 	if(time_it) CK(cudaEventRecord(s.ev[4], s.st));
 	s.d2h_recs = 0;
 	if(s.want_host) {
@@ -1807,6 +1918,11 @@ static int finish_batch(cfb_ctx* c, Slot& s, bool time_it, bool to_host, cfb_res
 		break;
 	}
 	const uint64_t nrec = s.h_scal.p[4];
+	if(s.folded) {        // the batch is final: add its counters to the context's totals (stream order keeps this ahead of any read)
+		const uint32_t n3 = 3 * c->cnt.n;
+		k_cnt_commit<<<(n3 + 255) / 256, 256, 0, s.st>>>(s.cnt.p, c->cnt.total.p, n3); c->launches++;
+		s.folded = false; c->cnt.reduced = false;
+	}
 	if(to_host) {
 		if(s.n_units) c->rec_ratio = std::max(c->rec_ratio * 0.98, (double)nrec / (double)s.n_units);
 		if(!s.want_host || nrec > s.d2h_recs) {       // not (fully) covered by the speculative copy
@@ -1829,7 +1945,7 @@ extern "C" int cfb_classify_submit(cfb_ctx* c, int slot, const cfb_batch* b) {
 	Slot& s = c->slots[slot];
 	if(s.pending) return fail(CFB_EINVAL, "slot %d still has an un-waited batch", slot);
 	int rc = stage_batch(c, s, b); if(rc) return rc;
-	s.cap = 0; s.want_host = true;
+	s.cap = 0; s.want_host = true; s.is_text = false;
 	rc = enqueue_kernels(c, s, 0, false); if(rc) return rc;
 	s.pending = true;
 	return CFB_OK;
@@ -1854,7 +1970,7 @@ extern "C" int cfb_batch_upload(cfb_ctx* c, const cfb_batch* b, cfb_dbatch** out
 	Slot& s = c->slots[kSlots - 1];
 	int rc = stage_batch(c, s, b); if(rc) return rc;
 	CK(cudaStreamSynchronize(s.st));
-	s.cap = 0;
+	s.cap = 0; s.is_text = false;
 	c->resident.slot = kSlots - 1; c->resident_used = true;
 	*out = &c->resident;
 	return CFB_OK;
@@ -1891,7 +2007,9 @@ extern "C" int cfb_ctx_counters(cfb_ctx* c, uint64_t out[8]) {
 	return CFB_OK;
 }
 
-extern "C" void* cfb_host_alloc(size_t bytes) { void* p = nullptr; if(cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; return p; }
+// pinned for every device of the process (several contexts on different GPUs may DMA from the same buffer pool)
+extern "C" void* cfb_host_alloc(size_t bytes) { void* p = nullptr; if(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+extern "C" int cfb_device_count(void) { int n = 0; if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 extern "C" void cfb_host_free(void* p) { if(p) cudaFreeHost(p); }
 
 extern "C" int cfb_test_lf(const cfb_index* ix, const uint64_t* rows, const uint8_t* chars, uint64_t n, uint64_t* out) {
@@ -1923,3 +2041,4 @@ extern "C" int cfb_test_resolve(const cfb_index* ix, const uint64_t* rows, uint6
 }
 
 #include "cf_text.cuh"
+#include "cf_multi.cuh"

@@ -193,12 +193,50 @@ int cfb_text_wait(cfb_ctx*, int slot, int discard, cfb_text_result* out);
  * n_obs1 = reads whose single best row reached the maximum score (observed keys of size 1). */
 int cfb_text_species(cfb_ctx*, uint64_t* taxid, uint64_t* n_reads, uint64_t* n_unique, uint64_t* n_obs1, uint64_t cap, uint64_t* n);
 
+/* ---- per-taxon counters and the multi-GPU reduction ---------------------------------
+ * Replaces: SpeciesMetrics::addSpeciesCounts (aln_sink.h:142-172) and, across GPUs, the dense part of
+ * SpeciesMetrics::merge (aln_sink.h:109-140; per-thread metrics summed at the end of the run, centrifuge.cpp:3175-3179).
+ * Every context keeps, on its device, {numReads, numUniqueReads, reads whose single best row reached the maximum
+ * score} for every taxid a report can mention (tree nodes, sequence taxids, 0 = unclassified, 1); the index space is
+ * cfb_counts_taxids (ascending).  The text operator always counts; the record-level entry points count when
+ * cfb_ctx_count_records is on (a kernel behind the classification kernels of each batch; batches add to the totals when
+ * they are waited for).  cfb_counts_allreduce is the path's one collective: ncclAllReduce(ncclUint64, ncclSum) of the
+ * totals over the communicator, NVLink/NVSwitch underneath.  The sparse tie sets that feed the EM (cfb_text_result.multi)
+ * are merged by the caller, as the reference merges `observed`. */
+int cfb_ctx_count_records(cfb_ctx*, int on);
+int cfb_counts_taxids(cfb_ctx*, uint64_t* taxid, uint64_t cap, uint64_t* n);
+int cfb_counts_reset(cfb_ctx*);
+/* entries with n_reads > 0; global = 0: this context's totals, 1: the totals of the last cfb_counts_allreduce */
+int cfb_counts_read(cfb_ctx*, int global, uint64_t* taxid, uint64_t* n_reads, uint64_t* n_unique, uint64_t* n_obs1, uint64_t cap, uint64_t* n);
+/* dense form: out[0..n) numReads, out[n..2n) numUniqueReads, out[2n..3n) observed singletons, n = cfb_counts_taxids */
+int cfb_counts_dense(cfb_ctx*, int global, uint64_t* out, uint64_t cap);
+/* Communicator: either one process per GPU (rank 0 calls cfb_comm_unique_id, ships the 128 bytes to the other ranks by
+ * whatever launcher plumbing it has, every rank calls cfb_comm_init_rank), or one process driving several GPUs
+ * (cfb_comm_init_all over its contexts, one per device; what `centrifuge-class --devices` does). */
+#define CFB_COMM_ID_BYTES 128
+int cfb_comm_unique_id(uint8_t id[CFB_COMM_ID_BYTES]);
+int cfb_comm_init_rank(cfb_ctx*, int nranks, int rank, const uint8_t id[CFB_COMM_ID_BYTES]);
+int cfb_comm_init_all(cfb_ctx* const* ctxs, int n);
+int cfb_comm_info(const cfb_ctx*, int* rank, int* size, int* nccl_version);
+/* ctxs = the calling process's contexts (n = 1 under torchrun/MPI); collective over the communicator.  dense_out
+ * (optional) receives the reduced dense vector (layout of cfb_counts_dense).  Without a communicator and n = 1 the
+ * "reduced" totals are the local ones. */
+int cfb_counts_allreduce(cfb_ctx* const* ctxs, int n, uint64_t* dense_out, uint64_t cap);
+
+/* Measurement hooks (bench.py): the product's own load requests of the last batch when the context was created with
+ * CFB_COUNT=2 -- {rank16 entries, 10-mer table entries, K-mer table entries, walk8 entries} -- and the random-gather
+ * ceiling of this device over the replica's own arrays: independent uniformly random gathers from table 0 = rank16
+ * (16 B), 1 = K-mer table (16 B), 2 = walk8 (8 B), 3 = resolve table (8 B), in G requests/s. */
+int cfb_ctx_requests(cfb_ctx*, uint64_t out[4]);
+int cfb_gather_ceiling(const cfb_index*, int table, uint64_t n_requests, double* g_requests_per_s, double* ms);
+
 /* Operation counters of the last batch on this ctx (same definition as SURVEY.md 8d):
  * {units, partial_searches, ftab_probes, sides_search, walk_steps, rows_resolved, lf_steps_total, ext_searches} */
 int cfb_ctx_counters(cfb_ctx*, uint64_t out[8]);
 int cfb_ctx_kernel_launches(const cfb_ctx*, uint64_t* n);
 
-void* cfb_host_alloc(size_t bytes);   /* pinned host memory */
+int   cfb_device_count(void);         /* usable CUDA devices (0 without a driver) */
+void* cfb_host_alloc(size_t bytes);   /* pinned host memory (portable: every device of the process can DMA from it) */
 void  cfb_host_free(void*);
 
 /* Device unit-test hooks (tests/ only): run the cooperative LF / resolve primitives on

@@ -39,6 +39,10 @@ int cfb_text_wait(cfb_ctx*, int, int, cfb_text_result*) { return CFB_ENODEV; }
 int cfb_text_species(cfb_ctx*, uint64_t*, uint64_t*, uint64_t*, uint64_t*, uint64_t, uint64_t* n) { if(n) *n = 0; return CFB_ENODEV; }
 int cfb_em_abundance(int, uint64_t, uint64_t, const uint64_t*, const uint64_t*, const uint32_t*, const uint64_t*, double*, uint64_t*, double*) { return CFB_ENODEV; }
 const char* cfb_em_last_error(void) { return "host stub: no device"; }
+int cfb_counts_read(cfb_ctx*, int, uint64_t*, uint64_t*, uint64_t*, uint64_t*, uint64_t, uint64_t* n) { if(n) *n = 0; return CFB_ENODEV; }
+int cfb_counts_allreduce(cfb_ctx* const*, int, uint64_t*, uint64_t) { return CFB_ENODEV; }
+int cfb_comm_init_all(cfb_ctx* const*, int) { return CFB_ENODEV; }
+int cfb_device_count(void) { return 0; }
 void* cfb_host_alloc(size_t n) { return malloc(n ? n : 1); }
 void cfb_host_free(void* p) { free(p); }
 }
