@@ -43,6 +43,11 @@ class BatchC(C.Structure):
                 ("off", C.POINTER(C.c_uint64) * 2), ("len", C.POINTER(C.c_uint32) * 2), ("flags", C.POINTER(C.c_uint8))]
 
 
+class BatchPackedC(C.Structure):
+    _fields_ = [("n_units", C.c_uint64), ("n_mates", C.c_int32), ("words", C.POINTER(C.c_uint64)), ("n_words", C.c_uint64),
+                ("len", C.POINTER(C.c_uint32) * 2), ("n_pos", C.POINTER(C.c_uint64)), ("n_n", C.c_uint64), ("flags", C.POINTER(C.c_uint8))]
+
+
 class ResultC(C.Structure):
     _fields_ = [("n_units", C.c_uint64), ("n_recs", C.c_uint64), ("rec_off", C.POINTER(C.c_uint32)), ("recs", C.c_void_p)]
 
@@ -135,6 +140,45 @@ def make_batch(bases, off1, len1, off2=None, len2=None, flags=None):
     return b
 
 
+def make_batch_packed(words, len1, len2=None, n_pos=None, flags=None):
+    b = BatchPackedC()
+    b.n_units = len(len1)
+    b.n_mates = 2 if len2 is not None else 1
+    b.words, b.n_words = _p(words, C.c_uint64), words.size
+    b.len[0] = _p(len1, C.c_uint32)
+    if len2 is not None:
+        b.len[1] = _p(len2, C.c_uint32)
+    if n_pos is not None and n_pos.size:
+        b.n_pos, b.n_n = _p(n_pos, C.c_uint64), n_pos.size
+    if flags is not None:
+        b.flags = _p(flags, C.c_uint8)
+    b._keep = (words, len1, len2, n_pos, flags)
+    return b
+
+
+def pack_batch(batch):
+    """cfb_pack_batch: (words, n_pos) of a byte-form BatchC"""
+    nw, nn = C.c_uint64(), C.c_uint64()
+    lib().cfb_pack_batch(C.byref(batch), None, C.c_uint64(0), None, C.c_uint64(0), C.byref(nw), C.byref(nn))
+    words = np.zeros(max(1, int(nw.value)), dtype=np.uint64); npos = np.zeros(max(1, int(nn.value)), dtype=np.uint64)
+    _ck(lib().cfb_pack_batch(C.byref(batch), _p(words, C.c_uint64), C.c_uint64(words.size), _p(npos, C.c_uint64), C.c_uint64(npos.size), C.byref(nw), C.byref(nn)))
+    return words[:int(nw.value)], npos[:int(nn.value)]
+
+
+def pack_fixed(codes):
+    """vectorised packing of an (n, L) code matrix (0..4): words (n * ceil(L/32),) and the N position list"""
+    n, L = codes.shape
+    W = (L + 31) // 32
+    pad = np.zeros((n, W * 32), dtype=np.uint64)
+    isn = codes > 3
+    pad[:, :L] = np.where(isn, 0, codes)
+    sh = (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, None, :]
+    words = (pad.reshape(n, W, 32) << sh).sum(axis=2, dtype=np.uint64).reshape(-1)
+    r, j = np.nonzero(isn)
+    npos = ((r.astype(np.uint64) * np.uint64(W) + (j // 32).astype(np.uint64)) << np.uint64(5)) | (j % 32).astype(np.uint64)
+    return np.ascontiguousarray(words), np.ascontiguousarray(npos)
+
+
 def pinned_array(shape, dtype):
     """numpy array backed by cfb_host_alloc (pinned) memory: H2D copies are DMA'd straight from it."""
     dt = np.dtype(dtype)
@@ -186,6 +230,9 @@ class Context:
     def submit(self, slot, batch):
         _ck(lib().cfb_classify_submit(self.h, C.c_int(slot), C.byref(batch)))
 
+    def submit_packed(self, slot, pbatch):
+        _ck(lib().cfb_classify_submit_packed(self.h, C.c_int(slot), C.byref(pbatch)))
+
     def wait(self, slot, copy=True):
         res = ResultC()
         _ck(lib().cfb_classify_wait(self.h, C.c_int(slot), C.byref(res)))
@@ -196,10 +243,13 @@ class Context:
         _ck(lib().cfb_batch_upload(self.h, C.byref(batch), C.byref(d)))
         return d
 
-    def classify_resident(self, dbatch):
+    def classify_resident(self, dbatch, first=None, count=None):
         ms = (C.c_float * 5)()
         nrec = C.c_uint64()
-        _ck(lib().cfb_classify_resident(self.h, dbatch, ms, C.byref(nrec)))
+        if first is None:
+            _ck(lib().cfb_classify_resident(self.h, dbatch, ms, C.byref(nrec)))
+        else:
+            _ck(lib().cfb_classify_resident_range(self.h, dbatch, C.c_uint64(first), C.c_uint64(count), ms, C.byref(nrec)))
         return list(ms), int(nrec.value)
 
     def resident_result(self):
@@ -368,6 +418,23 @@ def synth_reads(opts, n, rdlen, seed):
     if rc != 0:
         raise CfbError("cfb_synth_reads error %d: %s" % (rc, L.cfb_build_last_error().decode()))
     return out
+
+
+class SynthReadOpts(C.Structure):
+    _fields_ = [("len_lo", C.c_uint32), ("len_hi", C.c_uint32), ("paired", C.c_int32), ("ins_lo", C.c_uint32), ("ins_hi", C.c_uint32)]
+
+
+def synth_reads_ex(opts, n, seed, len_lo, len_hi, paired=False, ins=(200, 500)):
+    """-> codes (mates, n, len_hi) uint8 padded with 4, lens (mates, n) uint32"""
+    mates = 2 if paired else 1
+    ro = SynthReadOpts(len_lo, len_hi, 1 if paired else 0, ins[0], ins[1])
+    codes = np.zeros((mates, n, len_hi), dtype=np.uint8); lens = np.zeros((mates, n), dtype=np.uint32)
+    L = lib()
+    L.cfb_build_last_error.restype = C.c_char_p
+    rc = L.cfb_synth_reads_ex(C.byref(opts), C.byref(ro), C.c_uint64(n), C.c_uint64(seed), _p(codes, C.c_uint8), _p(lens, C.c_uint32))
+    if rc != 0:
+        raise CfbError("cfb_synth_reads_ex error %d: %s" % (rc, L.cfb_build_last_error().decode()))
+    return codes, lens
 
 
 def synth_fasta(opts, path):

@@ -765,6 +765,58 @@ extern "C" int cfb_synth_reads(const cfb_build_opts* o, uint64_t n, uint32_t rdl
 	return CFB_OK;
 }
 
+// Paired / mixed-length variant of the same recipe (2 x L PE with insert U[ins_lo, ins_hi] and mate 2 reverse-
+// complemented; U[len_lo, len_hi] read lengths).  codes: mate-major (mates, n, len_hi), rows padded with N; lens: (mates, n).
+__global__ void k_synth_reads_ex(SynthSpec sp, cfb_synth_read_opts ro, uint64_t n, uint64_t seed, uint8_t* out, uint32_t* lens) {
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(r >= n) return;
+	const uint64_t h0 = mix64(seed * 0x9E3779B97F4A7C15ull + r);
+	const bool random = (h0 & 0xffff) < 3277;                 // 5% units of random sequence
+	const uint32_t nseq = sp.genera * sp.species;
+	const uint32_t seq = (uint32_t)((h0 >> 16) % nseq);
+	const bool rc = (mix64(h0 ^ 0x77) & 1) != 0;
+	const uint32_t span = ro.len_hi - ro.len_lo + 1;
+	const int mates = ro.paired ? 2 : 1;
+	uint32_t L[2]; L[0] = ro.len_lo + (uint32_t)(mix64(h0 ^ 0xA1) % span); L[1] = ro.paired ? ro.len_lo + (uint32_t)(mix64(h0 ^ 0xA2) % span) : 0;
+	uint64_t frag = L[0];
+	if(ro.paired) { frag = ro.ins_lo + mix64(h0 ^ 0xA3) % (ro.ins_hi - ro.ins_lo + 1); if(frag < L[0]) frag = L[0]; if(frag < L[1]) frag = L[1]; }
+	if(frag > sp.len) frag = sp.len;
+	for(int m = 0; m < mates; m++) if(L[m] > frag) L[m] = (uint32_t)frag;
+	const uint64_t pos = mix64(h0 ^ 0x1234) % (sp.len - frag + 1);
+	// fragment base at offset q of the sequenced strand (the reverse strand reads the genome backwards, complemented)
+	auto frag_base = [&](uint64_t q) -> int { if(!rc) return synth_base(sp, seq, pos + q); return 3 - synth_base(sp, seq, pos + frag - 1 - q); };
+	for(int m = 0; m < mates; m++) {
+		uint8_t* o = out + ((uint64_t)m * n + r) * ro.len_hi;
+		lens[(uint64_t)m * n + r] = L[m];
+		for(uint32_t i = 0; i < ro.len_hi; i++) {
+			int c = 4;
+			if(i < L[m]) {
+				const uint64_t hi = mix64(h0 + 0x51ED27ull * (i + 1) + 0x9E37ull * (m + 1));
+				if(random) c = (int)(hi & 3);
+				else {
+					c = m == 0 ? frag_base(i) : 3 - frag_base(frag - 1 - i);       // mate 2: reverse complement of the fragment's far end
+					if(((hi >> 8) & 0xffff) < 655) c = (c + 1) & 3;          // 1% substitutions
+				}
+				if(((hi >> 32) & 0xffff) < 66) c = 4;                       // 0.1% N
+			}
+			o[i] = (uint8_t)c;
+		}
+	}
+}
+extern "C" int cfb_synth_reads_ex(const cfb_build_opts* o, const cfb_synth_read_opts* ro, uint64_t n, uint64_t read_seed, uint8_t* out_codes, uint32_t* out_lens) {
+	if(!o || !ro || !out_codes || !out_lens || ro->len_lo < 1 || ro->len_hi < ro->len_lo || o->synth_len < ro->len_hi || (ro->paired && (ro->ins_hi < ro->ins_lo || ro->ins_hi > o->synth_len)))
+		return bfail(CFB_EINVAL, "cfb_synth_reads_ex: bad arguments");
+	BCK(cudaSetDevice(o->device));
+	SynthSpec sp; sp.genera = o->synth_genera; sp.species = o->synth_species; sp.len = o->synth_len; sp.seed = o->synth_seed;
+	sp.div_q32 = (uint32_t)std::min(4294967295.0, o->synth_div * 4294967296.0);
+	const uint64_t mates = ro->paired ? 2 : 1;
+	Dev<uint8_t> d; BCK(d.alloc(n * mates * ro->len_hi)); Dev<uint32_t> dl; BCK(dl.alloc(n * mates));
+	k_synth_reads_ex<<<(unsigned)((n + 127) / 128), 128>>>(sp, *ro, n, read_seed, d.p, dl.p);
+	BCK(cudaMemcpy(out_codes, d.p, n * mates * ro->len_hi, cudaMemcpyDeviceToHost));
+	BCK(cudaMemcpy(out_lens, dl.p, n * mates * 4, cudaMemcpyDeviceToHost));
+	return CFB_OK;
+}
+
 // Materialise the synthetic genomes as FASTA (tests: byte-compare this builder with centrifuge-build-bin).
 extern "C" int cfb_synth_fasta(const cfb_build_opts* o, const char* path) {
 	if(!o || !path) return bfail(CFB_EINVAL, "null argument");

@@ -1029,20 +1029,21 @@ extern "C" int cfb_test_host_path(const char* index_base, const char* reads_a, c
 		o.prm.khits = khits; o.fasta = fasta != 0; o.seed = seed; o.trim5 = trim5; o.trim3 = trim3; o.report = out_report;
 		if(out_kreport) o.kreport = out_kreport;
 		const HostIndex& h = *cfb_index_host(ix);
-		FileIn fa, fb; const bool paired = reads_b != NULL;
-		if(!fa.open(reads_a) || (paired && !fb.open(reads_b))) throw 2;
+		// reads_a / reads_b are comma-separated file lists, read as cfb_run's record-level reader reads them
+		ListIn la, lb; const bool paired = reads_b != NULL;
+		la.files = split(reads_a, ','); if(paired) lb.files = split(reads_b, ',');
 		HostBatch hb; hb.clear(paired);
-		bool firstA = true, firstB = true; uint64_t cntA = 0, cntB = 0; Rec ra, rb;
+		uint64_t cntA = 0, cntB = 0; Rec ra, rb;
 		for(;;) {
-			const bool okA = o.fasta ? parse_fasta(fa, ra, cntA, firstA, o.trim5, o.trim3) : parse_fastq(fa, ra, cntA, firstA, o.trim5, o.trim3);
+			const bool okA = la.read(o.fasta, ra, cntA, o.trim5, o.trim3);
 			bool okB = true;
-			if(paired) okB = o.fasta ? parse_fasta(fb, rb, cntB, firstB, o.trim5, o.trim3) : parse_fastq(fb, rb, cntB, firstB, o.trim5, o.trim3);
+			if(paired) okB = lb.read(o.fasta, rb, cntB, o.trim5, o.trim3);
 			if(!okA && paired && okB) { std::cerr << "Error, fewer reads in file specified with -1 than in file specified with -2" << std::endl; throw 1; }
 			if(!okA) break;
 			if(!okB) { std::cerr << "Error, fewer reads in file specified with -2 than in file specified with -1" << std::endl; throw 1; }
 			hb.add(ra, paired ? &rb : NULL, o.seed);
 		}
-		fa.close(); fb.close();
+		la.close(); lb.close();
 		if(hb.n != n_units) throw 3;
 		cfb_result res; res.n_units = n_units; res.n_recs = rec_off[n_units]; res.rec_off = rec_off; res.recs = recs;
 		Species sp; Formatter fmt(h, o, sp); KReport kr(h, o);

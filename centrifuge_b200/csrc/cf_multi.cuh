@@ -151,7 +151,9 @@ extern "C" int cfb_counts_allreduce(cfb_ctx* const* ctxs, int n, uint64_t* dense
 		cfb_ctx* c = ctxs[i];
 		if(!c) return fail(CFB_EINVAL, "null context");
 		int rc = comm_prepare(c); if(rc) return rc;
-		CK(cudaDeviceSynchronize());         // every collected batch has committed its counters (commits run on the slots' streams)
+		// every collected batch has queued the commit of its counters on its slot's stream: order the collective behind
+		// those commits on the device, without draining batches that are still in flight
+		for(int k = 0; k < kSlots; k++) { Slot& s = c->slots[k]; if(s.commit_pending) { CK(cudaStreamWaitEvent(c->comm_st, s.ev[5], 0)); s.commit_pending = false; } }
 	}
 	bool any_comm = false;
 	for(int i = 0; i < n; i++) any_comm |= ctxs[i]->comm != nullptr;

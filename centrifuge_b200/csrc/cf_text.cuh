@@ -632,7 +632,8 @@ extern "C" int cfb_text_wait(cfb_ctx* c, int slot, int discard, cfb_text_result*
 			CK(cudaMemcpyAsync(t.h_multi.p, t.multi.p, n_multi * out->multi_stride * 8, cudaMemcpyDeviceToHost, s.st));
 			more = true;
 		}
-		if(!discard) { const uint32_t nsp3 = 3 * tc.tb.n_sp; k_sp_commit<<<(nsp3 + 255) / 256, 256, 0, s.st>>>(t.sp.p, c->cnt.total.p, nsp3); c->launches++; c->cnt.reduced = false; }
+		if(!discard) { const uint32_t nsp3 = 3 * tc.tb.n_sp; k_sp_commit<<<(nsp3 + 255) / 256, 256, 0, s.st>>>(t.sp.p, c->cnt.total.p, nsp3); c->launches++; c->cnt.reduced = false;
+			CK(cudaEventRecord(s.ev[5], s.st)); s.commit_pending = true; }
 		if(more) CK(cudaStreamSynchronize(s.st));
 		out->tsv = t.h_tsv.p; out->tsv_bytes = tsv; out->multi = (const uint64_t*)t.h_multi.p; out->n_multi = n_multi;
 		return CFB_OK;

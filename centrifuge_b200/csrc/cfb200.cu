@@ -1529,6 +1529,7 @@ struct Slot {
 	// inputs
 	HBuf<uint8_t> h_bases; HBuf<uint64_t> h_off; HBuf<uint32_t> h_len; HBuf<uint8_t> h_flags;
 	DBuf<uint8_t> d_bases; DBuf<uint64_t> d_off; DBuf<uint32_t> d_len; DBuf<uint8_t> d_flags;
+	HBuf<uint64_t> h_words; DBuf<uint64_t> d_words, d_npos, d_woff; DBuf<uint32_t> d_wlen;      // packed input (cfb_batch_packed)
 	// work
 	DBuf<uint64_t> pk; DBuf<uint32_t> nm;
 	DBuf<HitRec> hits; DBuf<uint32_t> nhits; DBuf<uint32_t> nrows; DBuf<uint64_t> row_off; DBuf<uint64_t> bsum;
@@ -1538,13 +1539,14 @@ struct Slot {
 	HBuf<unsigned long long> h_scal;
 	HBuf<OutRec> h_recs; HBuf<uint32_t> h_rec_off;
 	DBuf<unsigned long long> cnt;     // this batch's per-taxon counters (record path), added to the context's totals at wait time
-	bool folded = false, is_text = false;
+	bool folded = false, is_text = false, commit_pending = false;
 	// batch bookkeeping
 	BatchView bv; uint64_t n_units = 0, n_bases = 0; uint32_t maxlen = 0, cap = 0; uint64_t rows_cap = 0, dense_cap = 0;
 	bool pending = false, reran = false;
 	bool want_host = false; uint64_t d2h_recs = 0;     // records already copied to h_recs by the speculative D2H queued behind the kernels
 	void release() {
 		h_bases.release(); h_off.release(); h_len.release(); h_flags.release(); d_bases.release(); d_off.release(); d_len.release(); d_flags.release();
+		h_words.release(); d_words.release(); d_npos.release(); d_woff.release(); d_wlen.release();
 		pk.release(); nm.release(); hits.release(); nhits.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
 		sparse.release(); nout.release(); out_off.release(); dense.release(); rec_off32.release(); scal.release(); h_scal.release(); h_recs.release(); h_rec_off.release(); cnt.release();
 		for(int i = 0; i < 6; i++) if(ev[i]) cudaEventDestroy(ev[i]);
@@ -1552,7 +1554,7 @@ struct Slot {
 	}
 };
 
-struct cfb_dbatch { int slot; };
+struct cfb_dbatch { int slot; uint64_t n_units; };
 struct TextCtx;                       // cf_text.cuh
 static void text_release(cfb_ctx*);
 static void comm_release(cfb_ctx*);   // cf_multi.cuh
@@ -1801,6 +1803,94 @@ static int stage_batch(cfb_ctx* c, Slot& s, const cfb_batch* b) {
 	return CFB_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Packed input (cfb_batch_packed): 2 bits per base + a sparse list of N positions instead of 1 byte per base, lengths
+// instead of offsets -- about a third of the host->device bytes of cfb_batch.  The device expands it into the byte form
+// the per-unit kernels read: every mate gets a 32-byte aligned slot of ceil(len/32)*32 bytes, so byte address =
+// 32 * word index + base in word, for the unpack kernel and for the N list alike.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wlen(const uint32_t* len, uint64_t n, uint32_t* wlen) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n) wlen[i] = (len[i] + 31u) >> 5;
+}
+// thread per (mate slot, word k): 32 codes of one packed word -> 32 bytes
+__global__ void __launch_bounds__(256) k_unpack(const uint64_t* __restrict__ words, const uint64_t* __restrict__ woff, uint64_t wbase, const uint32_t* __restrict__ len,
+                                                uint64_t n, uint32_t W, uint8_t* bases, uint64_t* off) {
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= n * W) return;
+	const uint64_t i = t / W; const uint32_t k = (uint32_t)(t - i * W);
+	const uint64_t w0 = wbase + woff[i];
+	if(k == 0) off[i] = w0 * 32;
+	if(k * 32 >= len[i]) return;
+	const uint64_t w = __ldg(words + w0 + k);
+	uint32_t o[8];
+	#pragma unroll
+	for(int q = 0; q < 8; q++) {          // 4 codes -> 4 bytes
+		const uint32_t b = (uint32_t)(w >> (8 * q)) & 0xffu;
+		o[q] = (b & 3u) | ((b & 0xcu) << 6) | ((b & 0x30u) << 12) | ((b & 0xc0u) << 18);
+	}
+	uint4* dst = reinterpret_cast<uint4*>(bases + (w0 + k) * 32);
+	dst[0] = make_uint4(o[0], o[1], o[2], o[3]); dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+__global__ void __launch_bounds__(256) k_set_n(const uint64_t* npos, uint64_t n, uint8_t* bases, uint64_t limit) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n) { const uint64_t p = npos[i]; if(p < limit) bases[p] = 4; }
+}
+
+static int stage_batch_packed(cfb_ctx* c, Slot& s, const cfb_batch_packed* b) {
+	if(!b || b->n_mates < 1 || b->n_mates > 2 || !b->words || !b->len[0] || (b->n_mates == 2 && !b->len[1]) || (b->n_n && !b->n_pos))
+		return fail(CFB_EINVAL, "malformed cfb_batch_packed");
+	if(b->n_units >= (1ull << 30)) return fail(CFB_EINVAL, "batch too large (n_units must be < 2^30)");
+	const uint64_t n = b->n_units; const int nm = b->n_mates;
+	uint32_t maxlen = 0; uint64_t need_words = 0;
+	for(int m = 0; m < nm; m++) for(uint64_t i = 0; i < n; i++) { maxlen = std::max(maxlen, b->len[m][i]); need_words += ((uint64_t)b->len[m][i] + 31) >> 5; }
+	if(need_words != b->n_words) return fail(CFB_EINVAL, "cfb_batch_packed: n_words is %llu, the lengths need %llu", (unsigned long long)b->n_words, (unsigned long long)need_words);
+	if(maxlen > 60000) return fail(CFB_EINVAL, "read longer than 60000 bases");
+	const uint64_t scan_blocks = (n + kScanBlock * kScanPer - 1) / (kScanBlock * kScanPer);
+	CK(s.d_bases.ensure(b->n_words * 32 + 64)); CK(s.d_off.ensure(n * nm + 1)); CK(s.d_len.ensure(n * nm)); CK(s.d_flags.ensure(n));
+	CK(s.d_words.ensure(b->n_words + 1)); CK(s.d_npos.ensure(b->n_n + 1)); CK(s.d_wlen.ensure(n + 1)); CK(s.d_woff.ensure(n + 2)); CK(s.bsum.ensure(scan_blocks + 1));
+	auto pinned = [](const void* p) -> bool {
+		cudaPointerAttributes at;
+		if(cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+		return at.type == cudaMemoryTypeHost;
+	};
+	const uint64_t* src_words = b->words;
+	if(!pinned(b->words)) { CK(s.h_words.ensure(b->n_words)); memcpy(s.h_words.p, b->words, b->n_words * 8); src_words = s.h_words.p; }
+	CK(cudaMemcpyAsync(s.d_words.p, src_words, b->n_words * 8, cudaMemcpyHostToDevice, s.st));
+	CK(s.h_len.ensure(n * nm)); CK(s.h_flags.ensure(n));
+	for(int m = 0; m < nm; m++) {
+		const uint32_t* sl = b->len[m];
+		if(!pinned(sl)) { memcpy(s.h_len.p + m * n, sl, n * 4); sl = s.h_len.p + m * n; }
+		CK(cudaMemcpyAsync(s.d_len.p + m * n, sl, n * 4, cudaMemcpyHostToDevice, s.st));
+	}
+	if(b->n_n) {
+		const uint64_t* sp = b->n_pos;
+		if(!pinned(sp)) { CK(s.h_off.ensure(b->n_n)); memcpy(s.h_off.p, sp, b->n_n * 8); sp = s.h_off.p; }
+		CK(cudaMemcpyAsync(s.d_npos.p, sp, b->n_n * 8, cudaMemcpyHostToDevice, s.st));
+	}
+	if(b->flags && pinned(b->flags)) CK(cudaMemcpyAsync(s.d_flags.p, b->flags, n, cudaMemcpyHostToDevice, s.st));
+	else { if(b->flags) memcpy(s.h_flags.p, b->flags, n); else memset(s.h_flags.p, 3, n); CK(cudaMemcpyAsync(s.d_flags.p, s.h_flags.p, n, cudaMemcpyHostToDevice, s.st)); }
+	// expand on the device
+	const uint32_t W = (maxlen + 31) / 32;
+	uint64_t wbase = 0;
+	CK(cudaMemsetAsync(s.scal.p + 5, 0, 8, s.st));
+	for(int m = 0; m < nm && n; m++) {
+		k_wlen<<<(unsigned)((n + 255) / 256), 256, 0, s.st>>>(s.d_len.p + m * n, n, s.d_wlen.p);
+		k_scan_sums<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.d_wlen.p, n, s.bsum.p);
+		k_scan_top<<<1, 1024, 0, s.st>>>(s.bsum.p, scan_blocks, (uint64_t*)(s.scal.p + 5));
+		k_scan_apply<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.d_wlen.p, n, s.bsum.p, (const uint64_t*)(s.scal.p + 5), s.d_woff.p);
+		if(W) k_unpack<<<(unsigned)((n * W + 255) / 256), 256, 0, s.st>>>(s.d_words.p, s.d_woff.p, wbase, s.d_len.p + m * n, n, W, s.d_bases.p, s.d_off.p + m * n);
+		c->launches += 5;
+		for(uint64_t i = 0; i < n; i++) wbase += ((uint64_t)b->len[m][i] + 31) >> 5;      // mate 2 starts after all of mate 1 (host knows the lengths)
+	}
+	if(b->n_n) { k_set_n<<<(unsigned)((b->n_n + 255) / 256), 256, 0, s.st>>>(s.d_npos.p, b->n_n, s.d_bases.p, b->n_words * 32); c->launches++; }
+	CK(cudaGetLastError());
+	s.bv.bases = s.d_bases.p; s.bv.flags = s.d_flags.p; s.bv.n_units = (uint32_t)n; s.bv.n_mates = nm;
+	for(int m = 0; m < 2; m++) { s.bv.off[m] = m < nm ? s.d_off.p + m * n : nullptr; s.bv.len[m] = m < nm ? s.d_len.p + m * n : nullptr; }
+	s.n_units = n; s.n_bases = b->n_words * 32; s.maxlen = maxlen;
+	return CFB_OK;
+}
+
 // Enqueue all kernels of one batch on the slot's stream.  stage: 0 = from search, 1 = from k_rows
 // (after a rows-capacity overflow; the hit lists are already post-processed and sorted).
 static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
@@ -1921,6 +2011,7 @@ static int finish_batch(cfb_ctx* c, Slot& s, bool time_it, bool to_host, cfb_res
 	if(s.folded) {        // the batch is final: add its counters to the context's totals (stream order keeps this ahead of any read)
 		const uint32_t n3 = 3 * c->cnt.n;
 		k_cnt_commit<<<(n3 + 255) / 256, 256, 0, s.st>>>(s.cnt.p, c->cnt.total.p, n3); c->launches++;
+		CK(cudaEventRecord(s.ev[5], s.st)); s.commit_pending = true;       // cfb_counts_allreduce orders itself behind this event, without a host-side wait
 		s.folded = false; c->cnt.reduced = false;
 	}
 	if(to_host) {
@@ -1950,6 +2041,38 @@ extern "C" int cfb_classify_submit(cfb_ctx* c, int slot, const cfb_batch* b) {
 	s.pending = true;
 	return CFB_OK;
 }
+extern "C" int cfb_classify_submit_packed(cfb_ctx* c, int slot, const cfb_batch_packed* b) {
+	if(!c || slot < 0 || slot >= kSlots - 1) return fail(CFB_EINVAL, "bad ctx/slot");
+	CK(cudaSetDevice(c->ix->device));
+	Slot& s = c->slots[slot];
+	if(s.pending) return fail(CFB_EINVAL, "slot %d still has an un-waited batch", slot);
+	int rc = stage_batch_packed(c, s, b); if(rc) return rc;
+	s.cap = 0; s.want_host = true; s.is_text = false;
+	rc = enqueue_kernels(c, s, 0, false); if(rc) return rc;
+	s.pending = true;
+	return CFB_OK;
+}
+// Host helper: the packed form of a cfb_batch (single pass, one thread; callers that parse reads themselves can emit
+// the packed form directly).  Returns CFB_EINVAL when a capacity is too small; n_words / n_n always receive the sizes needed.
+extern "C" int cfb_pack_batch(const cfb_batch* in, uint64_t* words, uint64_t words_cap, uint64_t* n_pos, uint64_t npos_cap, uint64_t* n_words, uint64_t* n_n) {
+	if(!in || !n_words || !n_n || in->n_mates < 1 || in->n_mates > 2) return fail(CFB_EINVAL, "cfb_pack_batch: bad argument");
+	uint64_t w = 0, nn = 0; bool fits = true;
+	for(int m = 0; m < in->n_mates; m++) for(uint64_t i = 0; i < in->n_units; i++) {
+		const uint8_t* p = in->bases + in->off[m][i]; const uint32_t len = in->len[m][i];
+		for(uint32_t k = 0; k < len; k += 32) {
+			uint64_t v = 0; const uint32_t cnt = std::min<uint32_t>(32, len - k);
+			for(uint32_t j = 0; j < cnt; j++) {
+				const uint8_t c = p[k + j];
+				if(c > 3) { if(n_pos && nn < npos_cap) n_pos[nn] = (w << 5) | j; else fits = false; nn++; }
+				else v |= (uint64_t)c << (2 * j);
+			}
+			if(words && w < words_cap) words[w] = v; else fits = false;
+			w++;
+		}
+	}
+	*n_words = w; *n_n = nn;
+	return fits ? CFB_OK : fail(CFB_EINVAL, "cfb_pack_batch: buffers too small (%llu words, %llu N positions needed)", (unsigned long long)w, (unsigned long long)nn);
+}
 extern "C" int cfb_classify_wait(cfb_ctx* c, int slot, cfb_result* out) {
 	if(!c || slot < 0 || slot >= kSlots - 1 || !out) return fail(CFB_EINVAL, "bad ctx/slot");
 	CK(cudaSetDevice(c->ix->device));
@@ -1971,15 +2094,23 @@ extern "C" int cfb_batch_upload(cfb_ctx* c, const cfb_batch* b, cfb_dbatch** out
 	int rc = stage_batch(c, s, b); if(rc) return rc;
 	CK(cudaStreamSynchronize(s.st));
 	s.cap = 0; s.is_text = false;
-	c->resident.slot = kSlots - 1; c->resident_used = true;
+	c->resident.slot = kSlots - 1; c->resident.n_units = s.n_units; c->resident_used = true;
 	*out = &c->resident;
 	return CFB_OK;
 }
 extern "C" void cfb_dbatch_free(cfb_ctx* c, cfb_dbatch*) { if(c) c->resident_used = false; }
 extern "C" int cfb_classify_resident(cfb_ctx* c, cfb_dbatch* d, float* ms, uint64_t* n_recs) {
+	return cfb_classify_resident_range(c, d, 0, d ? d->n_units : 0, ms, n_recs);
+}
+extern "C" int cfb_classify_resident_range(cfb_ctx* c, cfb_dbatch* d, uint64_t first, uint64_t count, float* ms, uint64_t* n_recs) {
 	if(!c || !d) return fail(CFB_EINVAL, "null argument");
+	if(first + count > d->n_units) return fail(CFB_EINVAL, "cfb_classify_resident_range: units [%llu, %llu) exceed the uploaded batch", (unsigned long long)first, (unsigned long long)(first + count));
 	CK(cudaSetDevice(c->ix->device));
 	Slot& s = c->slots[d->slot];
+	// a window of the uploaded batch: offsets are absolute into the uploaded bases, so only the per-unit arrays shift
+	const uint64_t N = d->n_units; const int nmates = s.bv.n_mates;
+	s.bv.flags = s.d_flags.p + first; s.bv.n_units = (uint32_t)count; s.n_units = count;
+	for(int m = 0; m < nmates; m++) { s.bv.off[m] = s.d_off.p + m * N + first; s.bv.len[m] = s.d_len.p + m * N + first; }
 	int rc = enqueue_kernels(c, s, 0, true); if(rc) return rc;
 	cfb_result r;
 	rc = finish_batch(c, s, true, false, &r); if(rc) return rc;

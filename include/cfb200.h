@@ -146,6 +146,23 @@ int cfb_ctx_slots(const cfb_ctx*);
 int cfb_classify_submit(cfb_ctx*, int slot, const cfb_batch*);
 int cfb_classify_wait(cfb_ctx*, int slot, cfb_result* out);
 
+/* Packed form of a batch: a third of the host->device bytes of cfb_batch (about 37 instead of 113 bytes per 100 bp
+ * read), for callers that feed several GPUs from one host.  words: 2 bits per base (A=0 C=1 G=2 T=3), base j of a mate
+ * in bits 2*(j&31) of its word j>>5; every mate starts on a word boundary; layout = mate 1 of units 0..n-1, then
+ * mate 2 of units 0..n-1, so offsets are implied by the lengths (n_words must equal the sum of ceil(len/32)).
+ * n_pos: the positions that hold N instead of the packed code, (word index << 5) | base-in-word.
+ * Same results as the byte form (tests/test_gpu_parity.py).  cfb_pack_batch converts a cfb_batch on the host. */
+typedef struct {
+	uint64_t n_units;
+	int32_t  n_mates;
+	const uint64_t* words;  uint64_t n_words;
+	const uint32_t* len[2];
+	const uint64_t* n_pos;  uint64_t n_n;
+	const uint8_t*  flags;       /* as in cfb_batch */
+} cfb_batch_packed;
+int cfb_classify_submit_packed(cfb_ctx*, int slot, const cfb_batch_packed*);     /* collect with cfb_classify_wait */
+int cfb_pack_batch(const cfb_batch* in, uint64_t* words, uint64_t words_cap, uint64_t* n_pos, uint64_t npos_cap, uint64_t* n_words, uint64_t* n_n);
+
 /* Device-resident variant used by the roofline measurement: inputs already in HBM
  * (uploaded once by cfb_batch_upload), only kernels run.  kernel_ms (optional, 5 floats)
  * receives CUDA-event times of {search, prep+rows, resolve, score+compact, total}. */
@@ -153,6 +170,8 @@ typedef struct cfb_dbatch cfb_dbatch;
 int  cfb_batch_upload(cfb_ctx*, const cfb_batch*, cfb_dbatch** out);
 void cfb_dbatch_free(cfb_ctx*, cfb_dbatch*);
 int  cfb_classify_resident(cfb_ctx*, cfb_dbatch*, float* kernel_ms, uint64_t* n_recs);
+/* the same over units [first, first + count) of the uploaded batch (work buffers are sized by the window) */
+int  cfb_classify_resident_range(cfb_ctx*, cfb_dbatch*, uint64_t first, uint64_t count, float* kernel_ms, uint64_t* n_recs);
 /* copy the last resident result to host (for parity checks) */
 int  cfb_resident_result(cfb_ctx*, cfb_result* out);
 
@@ -281,6 +300,11 @@ const char* cfb_build_last_error(void);
  * position / strand, 1% substitutions, 0.1% N, 5% random reads (SURVEY.md 8d recipe). */
 int cfb_synth_reads(const cfb_build_opts* o, uint64_t n, uint32_t rdlen, uint64_t read_seed, uint8_t* out_codes);
 int cfb_synth_fasta(const cfb_build_opts* o, const char* path);
+/* The same recipe with lengths U[len_lo, len_hi] and, when paired, 2 mates per unit from a fragment of U[ins_lo, ins_hi]
+ * bases with mate 2 reverse-complemented (2 x 150 PE, insert 200-500; 75-300 bp mixed lengths).
+ * out_codes: (mates, n, len_hi) bytes, rows padded with 4; out_lens: (mates, n). */
+typedef struct { uint32_t len_lo, len_hi; int32_t paired; uint32_t ins_lo, ins_hi; } cfb_synth_read_opts;
+int cfb_synth_reads_ex(const cfb_build_opts* o, const cfb_synth_read_opts* ro, uint64_t n, uint64_t read_seed, uint8_t* out_codes, uint32_t* out_lens);
 
 /* ---- host driver (libcfb200_host): drop-in for `centrifuge-class` ------------------
  * Replaces: extern "C" int centrifuge(int argc, const char** argv) (centrifuge.cpp:3345).

@@ -47,3 +47,26 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
             if key.startswith(cname + ".") and not key.endswith(".size"):
                 assert getattr(st, key.split(".", 1)[1]).offset == off, key
     assert got["cfb_rec.size"] == rec.itemsize and got["cfb_rec.score"] == rec.fields["score"][1] and got["cfb_rec.uid"] == rec.fields["uid"][1]
+
+
+def test_host_packer_matches_a_numpy_restatement():
+    """cfb_pack_batch (host code, no device needed) == a vectorised numpy packing of the same reads."""
+    import numpy as np
+    from centrifuge_b200 import capi
+    rng = np.random.default_rng(3)
+    n, L = 500, 77
+    codes = rng.integers(0, 4, size=(n, L), dtype=np.uint8)
+    codes[rng.random((n, L)) < 0.02] = 4
+    offs = np.arange(n, dtype=np.uint64) * np.uint64(L); lens = np.full(n, L, dtype=np.uint32)
+    b = capi.make_batch(np.ascontiguousarray(codes.reshape(-1)), offs, lens)
+    words, npos = capi.pack_batch(b)
+    w2, p2 = capi.pack_fixed(codes)
+    assert np.array_equal(words, w2) and np.array_equal(npos, p2)
+    # unpack in numpy and compare with the input
+    W = (L + 31) // 32
+    un = ((words.reshape(n, W, 1) >> (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, None, :]) & np.uint64(3)).reshape(n, W * 32)[:, :L].astype(np.uint8)
+    un.reshape(-1)[0:0] = 0
+    flat = un.copy()
+    r = (npos >> np.uint64(5)) // np.uint64(W); j = ((npos >> np.uint64(5)) % np.uint64(W)) * np.uint64(32) + (npos & np.uint64(31))
+    flat[r.astype(np.int64), j.astype(np.int64)] = 4
+    assert np.array_equal(flat, codes)

@@ -25,6 +25,14 @@ def n_devices():
     return int(capi().lib().cfb_device_count())
 
 
+def first_diff(a, b):
+    la, lb = a.split(b"\n"), b.split(b"\n")
+    for i, (x, y) in enumerate(zip(la, lb)):
+        if x != y:
+            return "line %d: ours %r / reference %r (lines %d / %d)" % (i, x, y, len(la), len(lb))
+    return "lengths %d / %d" % (len(la), len(lb))
+
+
 def fastq_bytes(reads):
     return b"".join(b"@" + n.encode() + b"\n" + a.tobytes() + b"\n+\n" + b"I" * len(a) + b"\n" for n, a in reads)
 
@@ -108,7 +116,8 @@ def test_read_lists_keep_one_record_counter_and_pair_across_files(syn, tmp_path)
     args = ["-q", "-x", base, "-U", fa + "," + fb]
     want = util.run_cli(util.REF_CLASS, args, str(tmp_path / "r.tsv"), str(tmp_path / "r.rep"))
     got = util.run_cli(EXE, args, str(tmp_path / "o.tsv"), str(tmp_path / "o.rep"))
-    assert got == want
+    assert got[0] == want[0], first_diff(got[0], want[0])
+    assert got[1] == want[1], first_diff(got[1], want[1])
     m1 = [(n, a) for n, a in rd[:600]]; m2 = [(n, a[::-1].copy()) for n, a in rd[:600]]
     paths = {}
     for tag, lst, cut in (("a", m1, 250), ("b", m2, 400)):      # the -1 list is cut after 250 records, the -2 list after 400
@@ -119,7 +128,8 @@ def test_read_lists_keep_one_record_counter_and_pair_across_files(syn, tmp_path)
     args = ["-q", "-x", base, "-1", paths["a", 0] + "," + paths["a", 1], "-2", paths["b", 0] + "," + paths["b", 1]]
     want = util.run_cli(util.REF_CLASS, args, str(tmp_path / "r2.tsv"), str(tmp_path / "r2.rep"))
     got = util.run_cli(EXE, args, str(tmp_path / "o2.tsv"), str(tmp_path / "o2.rep"))
-    assert got == want
+    assert got[0] == want[0], first_diff(got[0], want[0])
+    assert got[1] == want[1], first_diff(got[1], want[1])
 
 
 @pytest.mark.skipif(n_devices() < 2, reason="needs two GPUs (gpurun --gpus 2)")

@@ -292,3 +292,35 @@ def test_large_batch_properties():
     for f in ("taxid", "score", "hitlen", "uid"):
         assert np.array_equal(orec[f], got[f]), f
     o.close(); ctx.close(); ix.close()
+
+
+def test_packed_input_gives_the_same_records():
+    """cfb_classify_submit_packed (2-bit words + N list + lengths) == cfb_classify_batch (1 byte per base), SE and PE,
+    ragged lengths incl. empty reads, reads that are all N, lengths on and off the 32-base word boundary."""
+    m = capi()
+    base = util.build_index("syn_a", 5, 4, 60000, seed=7, strains=True)
+    seqs = util.synth.make_genomes(5, 4, 60000, 7)
+    rd = [a for _, a in util.synth.sample_reads(seqs, 9000, 100, seed=71, lens=(1, 300), nrate=0.01)]
+    rd[5] = rd[5][:0]; rd[6] = np.full(64, ord("N"), dtype=np.uint8); rd[7] = rd[7][:32] if len(rd[7]) >= 32 else rd[7]; rd[8] = np.full(33, ord("N"), dtype=np.uint8)
+    ix = m.Index(base, 0); ctx = m.Context(ix)
+    b = util.Batch(rd)
+    cb = to_cbatch(b)
+    off0, rec0 = ctx.classify(cb)
+    words, npos = m.pack_batch(cb)
+    assert len(words) == int(((b.len1.astype(np.int64) + 31) // 32).sum()) and len(npos) == int((b.bases > 3).sum())
+    ctx.submit_packed(1, m.make_batch_packed(words, b.len1, None, npos, (b.flags & 1).astype(np.uint8)))
+    off1, rec1 = ctx.wait(1)
+    assert np.array_equal(off0, off1) and np.array_equal(rec0, rec1)
+    prs = util.synth.sample_pairs(seqs, 4000, 150, seed=72)
+    m1 = [x for _, x, _ in prs]; m2 = [y[: max(0, len(y) - (i % 50))] for i, (_, _, y) in enumerate(prs)]
+    bp = util.Batch(m1, m2)
+    cbp = to_cbatch(bp)
+    off0, rec0 = ctx.classify(cbp)
+    words, npos = m.pack_batch(cbp)
+    ctx.submit_packed(2, m.make_batch_packed(words, bp.len1, bp.len2, npos, (bp.flags & 3).astype(np.uint8)))
+    off1, rec1 = ctx.wait(2)
+    assert np.array_equal(off0, off1) and np.array_equal(rec0, rec1)
+    # malformed: n_words must follow from the lengths
+    with pytest.raises(m.CfbError):
+        ctx.submit_packed(3, m.make_batch_packed(words[:-1].copy(), bp.len1, bp.len2, npos, None))
+    ctx.close(); ix.close()
