@@ -146,8 +146,8 @@ int cfb_ctx_slots(const cfb_ctx*);
 int cfb_classify_submit(cfb_ctx*, int slot, const cfb_batch*);
 int cfb_classify_wait(cfb_ctx*, int slot, cfb_result* out);
 
-/* Packed form of a batch: a third of the host->device bytes of cfb_batch (about 37 instead of 113 bytes per 100 bp
- * read), for callers that feed several GPUs from one host.  words: 2 bits per base (A=0 C=1 G=2 T=3), base j of a mate
+/* Packed form of a batch: a third of the host->device bytes of the byte form -- about 37 instead of 113 bytes per
+ * 100 bp read -- for callers that feed several GPUs from one host.  words: 2 bits per base (A=0 C=1 G=2 T=3), base j of a mate
  * in bits 2*(j&31) of its word j>>5; every mate starts on a word boundary; layout = mate 1 of units 0..n-1, then
  * mate 2 of units 0..n-1, so offsets are implied by the lengths (n_words must equal the sum of ceil(len/32)).
  * n_pos: the positions that hold N instead of the packed code, (word index << 5) | base-in-word.
