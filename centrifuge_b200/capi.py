@@ -29,7 +29,7 @@ class IndexInfo(C.Structure):
 
 class IndexTables(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("sides_bytes", "sample_bytes", "rank16_bytes", "ftab2_bytes", "ftabk_bytes", "resolve_table_bytes",
-                                          "walk8_bytes", "total_bytes", "free_bytes_after_load")] + [("ftabk_chars", C.c_int32), ("resolve_entry_bytes", C.c_int32)]
+                                          "walk8_bytes", "total_bytes", "free_bytes_after_load", "walk8_rows")] + [("ftabk_chars", C.c_int32), ("resolve_entry_bytes", C.c_int32)]
 
 
 class Params(C.Structure):

@@ -24,5 +24,9 @@ int main(int argc, const char** argv) {
 		}
 		return last;
 	}
+	if(argc > 1 && strcmp(argv[1], "--promote") == 0) {   // centrifuge-promote <index> <tsv> <level> > out
+		if(argc != 5) { std::cerr << "Usage: centrifuge-class --promote centrifuge_index_name centrifuge_output level > output" << std::endl; return 1; }
+		return cfb_promote(argv[2], argv[3], argv[4], "-") == CFB_OK ? 0 : 1;
+	}
 	return cfb_run(argc, argv);
 }

@@ -842,8 +842,9 @@ struct TextPipe {
 	}
 };
 
-// One read list (-U a,b,c or the -1 / -2 lists) as the record-level reader sees it: the files one after another behind
-// one record counter, as BufferedFilePatternSource does (pat.h:786-811,883-904).
+// A list of read files behind one record counter, as BufferedFilePatternSource reads it (pat.h:786-811,883-904).
+// centrifuge-class feeds it one file at a time (see cfb_run), which is also what decides its messages: a file that
+// cannot be opened is the whole list, hence "No input read files were valid".
 struct ListIn {
 	std::vector<std::string> files; size_t next = 0; FileIn in; bool is_open = false, first = true;
 	bool open_next() {                  // BufferedFilePatternSource::open
@@ -1111,6 +1112,145 @@ extern "C" int cfb_kreport(const char* index_base, const char* tsv_path, const c
 	return rc;
 }
 
+// ------------------------------------------------------------------------------ centrifuge-promote
+// In-process equivalent of the reference's `centrifuge-promote` script: promote the taxIDs of a
+// classification TSV to a rank ("genus", "family", ...) or, with level "lca", merge every read's rows into their lowest
+// common ancestor.  Same bytes as the Perl script on the same TSV and index: rows of one read = consecutive rows with
+// the same first column (centrifuge-promote:156-172), fields re-split on runs of tabs (:106,149), string-keyed
+// taxonomy hashes fed by `centrifuge-inspect --taxonomy-tree` (:24-31), Perl's numeric / string comparison rules.
+namespace {
+struct Promote {
+	std::unordered_map<std::string, std::string> parent, level;   // keyed by the taxid as centrifuge-inspect prints it
+	std::string want;
+	static double num(const std::string& s) {                       // Perl numification: leading number, else 0
+		const char* p = s.c_str(); char* e = NULL;
+		while(*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r' || *p == '\f' || *p == '\v') p++;
+		const double v = strtod(p, &e);
+		if(e == p) return 0.0;
+		if(v != v) return 0.0;
+		return v;
+	}
+	static std::vector<std::string> split_plus(const std::string& s) {      // split /\t+/: runs of tabs separate, trailing empty fields go
+		std::vector<std::string> v; size_t i = 0; const size_t n = s.size();
+		if(n == 0) return v;
+		for(;;) {
+			size_t j = s.find('\t', i);
+			if(j == std::string::npos) { v.push_back(s.substr(i)); break; }
+			v.push_back(s.substr(i, j - i));
+			while(j < n && s[j] == '\t') j++;
+			if(j >= n) break;
+			i = j;
+		}
+		while(!v.empty() && v.back().empty()) v.pop_back();
+		return v;
+	}
+	static std::string first_col(const std::string& s) { const size_t j = s.find('\t'); return j == std::string::npos ? s : s.substr(0, j); }   // split /\t/ -> [0]
+	static std::string join(const std::vector<std::string>& c) { std::string o; for(size_t i = 0; i < c.size(); i++) { if(i) o.push_back('\t'); o += c[i]; } return o; }
+	// PromoteTaxId (:43-58); `def` tells whether the argument was a defined value (an undefined parent numifies to 0)
+	std::string promote(const std::string& tid, bool def) const {
+		if(!def || num(tid) <= 0) return "0";
+		std::unordered_map<std::string, std::string>::const_iterator lv = level.find(tid);
+		if(lv == level.end()) return "0";
+		if(lv->second == want) return tid;
+		if(num(tid) <= 1) return "0";
+		std::unordered_map<std::string, std::string>::const_iterator pa = parent.find(tid);
+		if(pa == parent.end()) return promote("", false);
+		return promote(pa->second, true);
+	}
+	std::string lca(std::string a, std::string b) const {            // :60-88 (`ge` is a STRING comparison, `>` a numeric one)
+		if(a == "0") return b;
+		if(b == "0") return a;
+		if(a == b) return a;
+		std::set<std::string> path;
+		while(a.compare("1") >= 0) {
+			path.insert(a);
+			std::unordered_map<std::string, std::string>::const_iterator pa = parent.find(a);
+			if(pa == parent.end()) { std::cerr << "Couldn't find parent of taxID " << a << " - directly assigned to root." << std::endl; break; }
+			if(a == pa->second) break;
+			a = pa->second;
+		}
+		while(num(b) > 1) {
+			if(path.count(b)) return b;
+			std::unordered_map<std::string, std::string>::const_iterator pb = parent.find(b);
+			if(pb == parent.end()) { std::cerr << "Couldn't find parent of taxID " << b << " - directly assigned to root." << std::endl; break; }
+			if(b == pb->second) break;
+			b = pb->second;
+		}
+		return "1";
+	}
+	void flush(const std::vector<std::string>& lines, FILE* fo) const {      // OutputPromotedLines :90-153
+		if(lines.empty()) return;
+		std::vector<std::string> out; unsigned long long matches = 0;
+		if(want != "lca") {
+			std::set<std::string> seen;
+			for(size_t i = 0; i < lines.size(); i++) {
+				std::vector<std::string> c = split_plus(lines[i]);
+				const bool has2 = c.size() > 2;
+				std::string nt = promote(has2 ? c[2] : std::string(), has2);
+				if(num(nt) <= 1) nt = has2 ? c[2] : std::string();
+				std::string nl = c.size() > 1 ? c[1] : std::string();
+				if(num(nt) >= 1) { std::unordered_map<std::string, std::string>::const_iterator lv = level.find(nt); if(lv != level.end()) nl = lv->second; }
+				if(!seen.insert(nt).second) continue;
+				matches++;
+				if(c.size() < 3) c.resize(3);
+				c[2] = nt; c[1] = nl;
+				out.push_back(join(c));
+			}
+		} else {
+			matches = 1;
+			std::vector<std::string> c = split_plus(lines[0]);
+			std::string l = c.size() > 2 ? c[2] : std::string();
+			for(size_t i = 1; i < lines.size(); i++) { std::vector<std::string> d = split_plus(lines[i]); l = lca(l, d.size() > 2 ? d[2] : std::string()); }
+			if(c.size() < 3) c.resize(3);
+			if(l != c[2]) { std::unordered_map<std::string, std::string>::const_iterator lv = level.find(l); c[1] = lv != level.end() ? lv->second : std::string(); }
+			c[2] = l;
+			out.push_back(join(c));
+		}
+		char nb[32]; snprintf(nb, sizeof nb, "%llu", matches);
+		for(size_t i = 0; i < out.size(); i++) {
+			std::vector<std::string> c = split_plus(out[i]);
+			if(c.empty()) c.push_back(nb); else c.back() = nb;
+			const std::string row = join(c);
+			fwrite(row.data(), 1, row.size(), fo); fputc('\n', fo);
+		}
+	}
+};
+}  // namespace
+
+// centrifuge-promote <index> <classification TSV> <level> > out   (out_path "-" = stdout).  Host only.
+extern "C" int cfb_promote(const char* index_base, const char* tsv_path, const char* level, const char* out_path) {
+	if(!index_base || !tsv_path || !level || !out_path) return CFB_EINVAL;
+	cfb_index* ix = NULL;
+	if(cfb_index_load(index_base, -1, &ix) != CFB_OK) return CFB_EIO;
+	int rc = CFB_OK;
+	{
+		const HostIndex& h = *cfb_index_host(ix);
+		Promote pr; pr.want = level;
+		for(size_t i = 0; i < h.nodes.size(); i++) {
+			char a[32], b[32]; snprintf(a, sizeof a, "%llu", (unsigned long long)h.nodes[i].taxid); snprintf(b, sizeof b, "%llu", (unsigned long long)h.nodes[i].parent);
+			pr.parent[a] = b; pr.level[a] = rank_name(h.nodes[i].rank);
+		}
+		std::ifstream in; std::istream* is = &std::cin;
+		if(strcmp(tsv_path, "-") != 0) { in.open(tsv_path, std::ios::binary); if(!in) rc = CFB_EIO; is = &in; }
+		FILE* fo = rc == CFB_OK ? (strcmp(out_path, "-") == 0 ? stdout : fopen(out_path, "wb")) : NULL;
+		if(rc == CFB_OK && !fo) rc = CFB_EIO;
+		if(rc == CFB_OK) {
+			std::string line;
+			if(std::getline(*is, line)) { fwrite(line.data(), 1, line.size(), fo); if(!is->eof()) fputc('\n', fo); }      // header, as read
+			std::string prev; std::vector<std::string> lines;
+			while(std::getline(*is, line)) {
+				const std::string id = Promote::first_col(line);
+				if(id == prev) lines.push_back(line);
+				else { prev = id; pr.flush(lines, fo); lines.clear(); lines.push_back(line); }
+			}
+			pr.flush(lines, fo);
+			if(fo != stdout) fclose(fo); else fflush(stdout);
+		}
+	}
+	cfb_index_free(ix);
+	return rc;
+}
+
 // everything a run owns, released on every way out (normal return, reader error -> throw 1, exception)
 struct RunState {
 	std::vector<cfb_index*> ix; std::vector<cfb_ctx*> ctx; FILE* fo = NULL;
@@ -1183,13 +1323,15 @@ extern "C" int cfb_run(int argc, const char** argv) {
 			busy[s] = true;
 			return true;
 		};
-		// The reference builds ONE pattern source per read list (all -1 files with all -2 files, then all -U files;
-		// pat.cpp:330-420): the record counter that names unnamed reads runs on across the files of a list, and mates
-		// keep pairing across file boundaries when the two lists are cut differently.
+		// Centrifuge handles its inputs one by one (centrifuge.cpp:3006-3046: "the name is not plural here"): every -1/-2
+		// file pair, then every -U file, gets a pattern source of its own, so the record counter that names unnamed reads
+		// and drives --skip/--upto restarts with every file and mate files must hold the same number of records pair by
+		// pair.  (bowtie2's one-source-per-list wiring in pat.cpp:330-420 is fed single-file lists; checked against the
+		// binary: unnamed reads of a second -U file are named 0, 1, ...)  The metrics run on across files (:3231).
 		struct Src { std::vector<std::string> a, b; bool paired; };
 		std::vector<Src> srcs;
-		if(!o.mates1.empty()) { Src s; s.a = o.mates1; s.b = o.mates2; s.paired = true; srcs.push_back(s); }
-		if(!o.singles.empty()) { Src s; s.a = o.singles; s.paired = false; srcs.push_back(s); }
+		for(size_t i = 0; i < o.mates1.size(); i++) { Src s; s.a.push_back(o.mates1[i]); s.b.push_back(o.mates2[i]); s.paired = true; srcs.push_back(s); }
+		for(size_t i = 0; i < o.singles.size(); i++) { Src s; s.a.push_back(o.singles[i]); s.paired = false; srcs.push_back(s); }
 		bool stop = false;
 		MultiObs multi; TextStats tstats; uint64_t host_units = 0;
 		TextPipe pipe(rs.ctx, o, fo, multi, tstats);

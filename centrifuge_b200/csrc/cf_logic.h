@@ -53,6 +53,7 @@ struct IndexView {
 	const uint32_t* rtab32;
 	const uint64_t* ftabk;          // device-only extended jump table: (top, bot) per K-mer, K = ftabk_chars (0 = absent)
 	const uint64_t* walk8;          // device-only: per SA row, the row 8 LF steps on | the 8 BWT bases met << 40 | #valid steps << 56 (null = absent)
+	uint64_t walk8_rows;            // rows [0, walk8_rows) have a walk8 entry (the table may cover a prefix of the rows when HBM is short)
 	uint64_t len, zoff, zside, fchr[4], last_boundary, num_sides, num_blocks;
 	uint32_t zoffc, n_boundaries, n_seqs, n_host;
 	int32_t  off_rate, ftab_chars, bshift, ftabk_chars;
@@ -96,6 +97,13 @@ CFB_HD uint64_t match2(uint64_t w, int c) {
 }
 
 CFB_HD int bwt_char(const IndexView& v, uint64_t row) {
+#ifdef __CUDA_ARCH__
+	if(v.rank16) {     // device replica: the indicator bits of the row's 64-row block (one 64-byte chunk); the '$' row has no bit and reads as A, as the file stores it
+		const uint64_t* e = v.rank16 + (row >> 6) * 8;
+		const uint32_t o = (uint32_t)(row & 63);
+		return (int)(((e[3] >> o) & 1ull) * 1 + ((e[5] >> o) & 1ull) * 2 + ((e[7] >> o) & 1ull) * 3);
+	}
+#endif
 	uint64_t s = row / 384; uint32_t off = (uint32_t)(row - s * 384);
 	return (int)((v.sides[s * 16 + (off >> 5)] >> ((off & 31) * 2)) & 3);
 }
@@ -104,6 +112,12 @@ CFB_HD int bwt_char(const IndexView& v, uint64_t row) {
 // (countBt2Side bt2_idx.h:2192-2227, countUpTo :2364-2425).  Scalar version: one thread reads
 // the words it needs.
 CFB_HD uint64_t lf_scalar(const IndexView& v, uint64_t row, int c) {
+#ifdef __CUDA_ARCH__
+	if(v.rank16) {     // device replica: one 16-byte rank16 entry (occ before the block, '$' excluded | indicator bits), same value as below
+		const uint64_t* e = v.rank16 + ((row >> 6) * 4 + (uint64_t)c) * 2;
+		return v.fchr[c] + (e[0] & 0x7fffffffffffffffull) + (uint64_t)popc64(e[1] & (((uint64_t)1 << (row & 63)) - 1));
+	}
+#endif
 	uint64_t s = row / 384; uint32_t off = (uint32_t)(row - s * 384);
 	const uint64_t* w = v.sides + s * 16;
 	uint32_t full = off >> 5, rem = off & 31;

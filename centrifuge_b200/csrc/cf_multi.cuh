@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(128) k_gather_probe(const unsigned long long* 
 			else v[k][0] = __ldg(a + u);
 		}
 		#pragma unroll
-		for(int k = 0; k < ILP; k++) acc += v[k][0] ^ v[k][W - 1];
+		for(int k = 0; k < ILP; k++) acc += W == 2 ? (v[k][0] ^ (v[k][W - 1] << 1)) : v[k][0];
 	}
 	if(acc == 0x123456789abcull) *sink = acc;
 }

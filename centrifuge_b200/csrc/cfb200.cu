@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 			c = rd.base(dep);
 			if(c <= 3) {
 				range = (bot - top) != 1;
-				if(w8 && (bot - top) <= (uint64_t)kJumpRows && dep >= slow_until && rlen - dep >= 8) {
+				if(w8 && (bot - top) <= (uint64_t)kJumpRows && dep >= slow_until && rlen - dep >= 8 && bot <= a.v.walk8_rows) {
 					// eight steps in one gather: a single row, or a narrow range whose rows (consecutive walk8 entries, one
 					// or two sectors) all continue with the read's next eight bases -- LF keeps such rows adjacent
 					jump = true; e.x = __ldg(w8 + top); e.y = 0; if(COUNT == 2) q_w8++;
@@ -1422,11 +1422,26 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 			CK(cudaDeviceSynchronize());
 			v.rank16 = r16; v.ftab2 = f2;
 			ix->tables.rank16_bytes = (nb + 1) * 64; ix->tables.ftab2_bytes = nf * 16;
-			// extended jump table: K = largest value with 4^K <= len/4 (most K-mers occur), capped at 15 and by free HBM
+			// The file's sides have served their purpose (rank16 holds the same information, and the rare scalar LF of the
+			// extension step reads rank16 too): free them unless the sides-based A/B kernels and test hooks are wanted
+			// (small indexes keep them; CFB_KEEP_SIDES=1 / CFB_LEGACY_LAYOUTS=1 force it).
+			if(ix->tables.sides_bytes > (256ull << 20) && !getenv("CFB_KEEP_SIDES") && !getenv("CFB_LEGACY_LAYOUTS")) {
+				cudaFree((void*)v.sides);
+				for(size_t i = 0; i < ix->dptrs.size(); i++) if(ix->dptrs[i] == (void*)v.sides) { ix->dptrs.erase(ix->dptrs.begin() + i); break; }
+				ix->device_bytes -= ix->tables.sides_bytes; ix->tables.sides_bytes = 0; v.sides = nullptr;
+			}
+			// HBM budget of the derived tables: what is free now minus the head-room the batch buffers need (24 GB by default:
+			// 16 slots of 0.5 M reads at ~3.5 KB each; CFB_HBM_HEADROOM_GB).  Tables are built in the order of gathers saved per
+			// byte -- K-mer jump table, resolve table, walk8 -- each only if it fits what is left; walk8, whose rows are hit
+			// uniformly, may cover just a prefix of the rows (a jump needs an entry for the row it starts from only).
+			size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+			double head_gb = 24.0; { const char* e = getenv("CFB_HBM_HEADROOM_GB"); if(e) head_gb = atof(e); }
+			const uint64_t headroom = std::min<uint64_t>((uint64_t)(head_gb * 1073741824.0), free_b / 2);
+			auto budget = [&]() -> uint64_t { size_t f = 0, t = 0; cudaMemGetInfo(&f, &t); return f > headroom ? f - headroom : 0; };
+			// extended jump table: K = largest value with 4^K <= len/4 (most K-mers occur), capped at 15 and by the budget
 			int K = 0;
 			{ const char* e = getenv("CFB_FTABK"); if(e) K = atoi(e); else { K = h.ftab_chars; while(K < 15 && (4ull << (2 * K)) <= h.len / 4) K++; } }
-			size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-			while(K > h.ftab_chars && (16ull << (2 * K)) > free_b / 3) K--;
+			while(K > h.ftab_chars && (16ull << (2 * K)) > budget() / 2) K--;
 			if(K > h.ftab_chars && K <= 16) {
 				uint64_t* fk = nullptr; const uint64_t nk = 1ull << (2 * K);
 				CK(cudaMalloc((void**)&fk, nk * 16));
@@ -1436,12 +1451,11 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 				v.ftabk = fk; v.ftabk_chars = K;
 				ix->tables.ftabk_bytes = nk * 16; ix->tables.ftabk_chars = K;
 			}
-			// resolve table: sequence id of every SA row (walked once here), if it fits comfortably
+			// resolve table: sequence id of every SA row (walked once here)
 			{
 				const char* e = (flags & CFB_LOAD_NO_RESOLVE_TABLE) ? "0" : getenv("CFB_RESOLVE_TABLE");
 				const uint64_t nrows = h.len + 1, esz = h.wide_sample ? 4 : 2;
-				cudaMemGetInfo(&free_b, &total_b);
-				if(!(e && e[0] == '0') && nrows * esz < free_b / 3) {
+				if(!(e && e[0] == '0') && nrows * esz + 16 <= budget()) {
 					void* tab = nullptr; unsigned long long* sc = nullptr;
 					CK(cudaMalloc(&tab, nrows * esz + 16)); CK(cudaMalloc((void**)&sc, 16));
 					ix->dptrs.push_back(tab); ix->device_bytes += nrows * esz;
@@ -1457,20 +1471,21 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 					ix->tables.resolve_table_bytes = nrows * esz; ix->tables.resolve_entry_bytes = (int32_t)esz;
 				}
 			}
-			// walk8: eight single-row LF steps per gather, if 8 bytes per row still leave room for the batch buffers
+			// walk8: eight single-row LF steps per gather, for as many rows as the budget allows (at least an eighth of them)
 			{
 				const char* e = (flags & CFB_LOAD_NO_WALK8) ? "0" : getenv("CFB_WALK8");
 				const uint64_t nrows = h.len + 1;
-				cudaMemGetInfo(&free_b, &total_b);
-				if(!(e && e[0] == '0') && nrows < (1ull << 40) && nrows * 8 + (24ull << 30) < free_b) {
+				uint64_t cover = std::min<uint64_t>(nrows, budget() / 8);
+				{ const char* f = getenv("CFB_WALK8_ROWS"); if(f) cover = std::min<uint64_t>(nrows, strtoull(f, NULL, 10)); }     // tests: force a partial table
+				if(!(e && e[0] == '0') && nrows < (1ull << 40) && cover >= nrows / 8 && cover > 0) {
 					void* tab = nullptr;
-					CK(cudaMalloc(&tab, nrows * 8 + 16));
-					ix->dptrs.push_back(tab); ix->device_bytes += nrows * 8;
+					CK(cudaMalloc(&tab, cover * 8 + 16));
+					ix->dptrs.push_back(tab); ix->device_bytes += cover * 8;
 					int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_build_walk8, kSearchThreads, 0);
-					k_build_walk8<<<prop.multiProcessorCount * std::max(occ, 1) * 4, kSearchThreads>>>(v, nrows, (uint64_t*)tab);
+					k_build_walk8<<<prop.multiProcessorCount * std::max(occ, 1) * 4, kSearchThreads>>>(v, cover, (uint64_t*)tab);
 					CK(cudaDeviceSynchronize());
-					v.walk8 = (const uint64_t*)tab;
-					ix->tables.walk8_bytes = nrows * 8;
+					v.walk8 = (const uint64_t*)tab; v.walk8_rows = cover;
+					ix->tables.walk8_bytes = cover * 8; ix->tables.walk8_rows = cover;
 				}
 			}
 		}
@@ -1668,11 +1683,13 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 	}
 	int occ = 0;
 	{ const char* g = getenv("CFB_GROUP"); if(g) { const int v = atoi(g); if(v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->group = v; } }
+	if(c->group != 1 && !c->view.sides) { cfb_ctx_destroy(c); return fail(CFB_EINVAL, "CFB_GROUP=%d needs the sides resident (CFB_KEEP_SIDES=1)", c->group); }
 	CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel(c->group, false), kSearchThreads, 0));
 	c->search_blocks = ix->sm_count * std::max(occ, 1);
 	{ const char* g = getenv("CFB_RESOLVE"); if(g) c->resolve_mode = atoi(g); else if(c->view.rtab16 || c->view.rtab32) c->resolve_mode = 3; }
 	if(c->resolve_mode == 3 && !(c->view.rtab16 || c->view.rtab32)) c->resolve_mode = 2;
 	if(c->resolve_mode == 1 && !c->view.blocks) c->resolve_mode = 2;
+	if(c->resolve_mode == 0 && !c->view.sides) c->resolve_mode = 2;
 	if(c->resolve_mode >= 2) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_c<false, false>, kSearchThreads, 0));
 	else if(c->resolve_mode == 1) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_t<false>, kSearchThreads, 0));
 	else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
@@ -2145,6 +2162,7 @@ extern "C" void cfb_host_free(void* p) { if(p) cudaFreeHost(p); }
 
 extern "C" int cfb_test_lf(const cfb_index* ix, const uint64_t* rows, const uint8_t* chars, uint64_t n, uint64_t* out) {
 	if(!ix || ix->device < 0) return fail(CFB_ENODEV, "no device");
+	if(!ix->view.sides) return fail(CFB_EINVAL, "the sides are not resident on this replica (CFB_KEEP_SIDES=1 keeps them)");
 	CK(cudaSetDevice(ix->device));
 	uint64_t *dr = nullptr, *dout = nullptr; uint8_t* dc = nullptr;
 	CK(cudaMalloc(&dr, n * 8 + 8)); CK(cudaMalloc(&dout, n * 8 + 8)); CK(cudaMalloc(&dc, n + 8));
@@ -2157,6 +2175,7 @@ extern "C" int cfb_test_lf(const cfb_index* ix, const uint64_t* rows, const uint
 }
 extern "C" int cfb_test_resolve(const cfb_index* ix, const uint64_t* rows, uint64_t n, uint32_t* out) {
 	if(!ix || ix->device < 0) return fail(CFB_ENODEV, "no device");
+	if(!ix->view.sides) return fail(CFB_EINVAL, "the sides are not resident on this replica (CFB_KEEP_SIDES=1 keeps them)");
 	CK(cudaSetDevice(ix->device));
 	uint64_t* dr = nullptr; uint32_t* dout = nullptr; unsigned long long* sc = nullptr;
 	CK(cudaMalloc(&dr, n * 8 + 8)); CK(cudaMalloc(&dout, n * 4 + 8)); CK(cudaMalloc(&sc, 16));

@@ -66,11 +66,14 @@ typedef struct {
 int cfb_index_get_info(const cfb_index*, cfb_index_info* out);
 
 /* What the device replica holds (bytes of HBM each; 0 = not built).  The derived tables are built at load time in
- * this order of benefit per byte, each only while it fits the budget left after the batch head-room:
- * rank16 + ftab2 (always), the K-mer jump table, the resolve table, walk8. */
+ * this order of benefit per byte, each only while it fits the budget left after the batch head-room (24 GB unless
+ * CFB_HBM_HEADROOM_GB says otherwise): rank16 + ftab2 (always), the K-mer jump table, the resolve
+ * table, walk8 (possibly for a prefix of the rows).  The file's sides are dropped once rank16 exists (sides_bytes = 0)
+ * except on small indexes, where the sides-based A/B kernels and test hooks stay usable. */
 typedef struct {
 	uint64_t sides_bytes, sample_bytes, rank16_bytes, ftab2_bytes, ftabk_bytes, resolve_table_bytes, walk8_bytes;
 	uint64_t total_bytes, free_bytes_after_load;
+	uint64_t walk8_rows;            /* rows [0, walk8_rows) have a walk8 entry (all rows when HBM allows, else a prefix) */
 	int32_t  ftabk_chars;           /* K of the jump table, 0 = none */
 	int32_t  resolve_entry_bytes;   /* 2 or 4, 0 = no resolve table (rows are resolved by walking) */
 } cfb_index_tables;
@@ -332,6 +335,12 @@ int cfb_em_abundance_host(uint64_t n, uint64_t K, const uint64_t* count, const u
  * --kreport-min-score N, --kreport-min-length N) from the rows while they are still in memory.  Host only. */
 int cfb_kreport(const char* index_base, const char* tsv_path, const char* out_path, int show_zeros,
                 int has_min_score, long long min_score, int has_min_length, long long min_length);
+
+/* Promote the taxIDs of a classification TSV to a taxonomic level, or merge every read's rows into their lowest common
+ * ancestor with level "lca" (SURVEY.md 8f rank 4).  Replaces the `centrifuge-promote` script (centrifuge-promote:1-175):
+ * same bytes from the same TSV and index; tsv_path / out_path "-" = stdin / stdout.  Host only.  The drop-in binary
+ * runs it as `centrifuge-class --promote <index> <tsv> <level>`. */
+int cfb_promote(const char* index_base, const char* tsv_path, const char* level, const char* out_path);
 
 #ifdef __cplusplus
 }

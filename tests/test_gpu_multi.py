@@ -103,21 +103,22 @@ def test_allreduce_on_a_communicator_of_one(syn):
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref reference binaries not shipped")
-def test_read_lists_keep_one_record_counter_and_pair_across_files(syn, tmp_path):
-    """-U a,b and -1 a1,a2 -2 b1,b2 are ONE pattern source per list in the reference (pat.cpp:330-420): unnamed reads are
-    numbered across files and mates keep pairing when the two lists are cut at different records."""
+def test_read_files_are_separate_pattern_sources(syn, tmp_path):
+    """Centrifuge runs its inputs one file (pair) at a time (centrifuge.cpp:3006-3046): unnamed reads of a second -U file
+    are numbered from 0 again, the report covers all files, and -1/-2 lists must match file by file."""
     base, reads = syn
     rd = reads[:900]
     fa, fb = str(tmp_path / "a.fq"), str(tmp_path / "b.fq")
     with open(fa, "wb") as f:
         f.write(fastq_bytes(rd[:500]))
-    with open(fb, "wb") as f:                                   # unnamed reads: their ids come from the list's record counter
+    with open(fb, "wb") as f:                                   # unnamed reads: their ids come from the file's own record counter
         f.write(b"".join(b"@\n" + a.tobytes() + b"\n+\n" + b"I" * len(a) + b"\n" for _, a in rd[500:]))
-    args = ["-q", "-x", base, "-U", fa + "," + fb]
-    want = util.run_cli(util.REF_CLASS, args, str(tmp_path / "r.tsv"), str(tmp_path / "r.rep"))
-    got = util.run_cli(EXE, args, str(tmp_path / "o.tsv"), str(tmp_path / "o.rep"))
-    assert got[0] == want[0], first_diff(got[0], want[0])
-    assert got[1] == want[1], first_diff(got[1], want[1])
+    for extra in ([], ["--host-parse"]):
+        args = ["-q", "-x", base, "-U", fa + "," + fb] + extra
+        want = util.run_cli(util.REF_CLASS, args[:5], str(tmp_path / "r.tsv"), str(tmp_path / "r.rep"))
+        got = util.run_cli(EXE, args, str(tmp_path / "o.tsv"), str(tmp_path / "o.rep"))
+        assert got[0] == want[0], first_diff(got[0], want[0])
+        assert got[1] == want[1], first_diff(got[1], want[1])
     m1 = [(n, a) for n, a in rd[:600]]; m2 = [(n, a[::-1].copy()) for n, a in rd[:600]]
     paths = {}
     for tag, lst, cut in (("a", m1, 250), ("b", m2, 400)):      # the -1 list is cut after 250 records, the -2 list after 400
@@ -126,6 +127,16 @@ def test_read_lists_keep_one_record_counter_and_pair_across_files(syn, tmp_path)
             with open(paths[tag, k], "wb") as f:
                 f.write(fastq_bytes(part))
     args = ["-q", "-x", base, "-1", paths["a", 0] + "," + paths["a", 1], "-2", paths["b", 0] + "," + paths["b", 1]]
+    for exe in (util.REF_CLASS, EXE):
+        p = subprocess.run([exe] + args + ["-S", str(tmp_path / "x.tsv"), "--report-file", str(tmp_path / "x.rep")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        assert p.returncode != 0 and b"fewer reads in file specified with -1" in p.stderr
+    # equal cuts: two file pairs, one after the other
+    for tag, lst in (("c", m1), ("d", m2)):
+        for k, part in enumerate((lst[:300], lst[300:])):
+            paths[tag, k] = str(tmp_path / ("%s%d.fq" % (tag, k)))
+            with open(paths[tag, k], "wb") as f:
+                f.write(fastq_bytes(part))
+    args = ["-q", "-x", base, "-1", paths["c", 0] + "," + paths["c", 1], "-2", paths["d", 0] + "," + paths["d", 1], "-U", fb]
     want = util.run_cli(util.REF_CLASS, args, str(tmp_path / "r2.tsv"), str(tmp_path / "r2.rep"))
     got = util.run_cli(EXE, args, str(tmp_path / "o2.tsv"), str(tmp_path / "o2.rep"))
     assert got[0] == want[0], first_diff(got[0], want[0])

@@ -80,44 +80,3 @@ def test_host_side_reproduces_reference_bytes_around_oracle_records(tmp_path):
             if os.path.exists(fpath):
                 os.remove(fpath)
     o.close()
-
-
-def test_read_lists_are_one_pattern_source(tmp_path):
-    """-U a,b and -1 a1,a2 -2 b1,b2: one record counter per list (names of unnamed reads run on across files) and mates
-    keep pairing across file boundaries when the two lists are cut at different records (pat.cpp:330-420, pat.h:786-811)."""
-    util.ensure_oracle()
-    from centrifuge_b200.build import build
-    build()
-    base = util.golden_index("adv")
-    lib = C.CDLL(util.PRODUCT_LIB)
-    reads = clean_reads()
-    o = util.Oracle(base)
-    rng = random.Random(5)
-    rs = make_reads(rng, reads)[:120]
-
-    def fq(path, part, unnamed=False):
-        with open(path, "wb") as f:
-            for n, s in part:
-                f.write(b"@" + (b"" if unnamed else n) + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
-
-    def run(p1, p2, units):
-        bt = util.Batch([np.frombuffer(s, dtype=np.uint8) for s in units[0]], [np.frombuffer(s, dtype=np.uint8) for s in units[1]] if p2 else None)
-        on, orec, _ = o.classify(bt, util.make_oparams())
-        rec_off = np.concatenate([[0], np.cumsum(on)]).astype(np.uint32); recs = np.ascontiguousarray(orec)
-        tsv, rep = str(tmp_path / "p.tsv"), str(tmp_path / "p.rep")
-        rc = lib.cfb_test_host_path(base.encode(), p1.encode(), p2.encode() if p2 else None, C.c_int(0), C.c_int(5), C.c_uint32(0), C.c_int(0), C.c_int(0),
-                                    rec_off.ctypes.data_as(C.POINTER(C.c_uint32)), recs.ctypes.data_as(C.c_void_p), C.c_uint64(len(on)), tsv.encode(), rep.encode(), None)
-        assert rc == 0, rc
-        args = ["-q", "-x", base] + (["-1", p1, "-2", p2] if p2 else ["-U", p1])
-        want = util.run_cli(util.REF_CLASS, args, str(tmp_path / "r.tsv"), str(tmp_path / "r.rep"))
-        with open(tsv, "rb") as f, open(rep, "rb") as g:
-            assert (f.read(), g.read()) == want
-
-    a, b = str(tmp_path / "a.fq"), str(tmp_path / "b.fq")
-    fq(a, rs[:70]); fq(b, rs[70:], unnamed=True)
-    run(a + "," + b, None, ([s for _, s in rs], None))
-    m2 = [(n, s[::-1]) for n, s in rs]
-    a1, a2, b1, b2 = (str(tmp_path / x) for x in ("a1.fq", "a2.fq", "b1.fq", "b2.fq"))
-    fq(a1, rs[:40]); fq(a2, rs[40:]); fq(b1, m2[:90]); fq(b2, m2[90:])
-    run(a1 + "," + a2, b1 + "," + b2, ([s for _, s in rs], [s for _, s in m2]))
-    o.close()
