@@ -302,7 +302,7 @@ def parity_check(a, ctx, ix, base, d, rd, nsample):
     from centrifuge_b200 import capi
     import pandas as pd
     tb = ix.tables()
-    tables = {"ftabk": tb["ftabk_chars"], "rtab": 8 * tb["resolve_entry_bytes"], "walk8": tb["walk8_bytes"] > 0, "walk8_row_coverage": tb["walk8_rows"] / float(ix.info.len + 1),
+    tables = {"ftabk": tb["ftabk_chars"], "ftabd": tb["ftabd_chars"], "rtab": 8 * tb["resolve_entry_bytes"], "walk8": tb["walk8_bytes"] > 0, "walk8_row_coverage": tb["walk8_rows"] / float(ix.info.len + 1),
               "compressed": bool(ix.info.compressed), "rows_beyond_2^32": bool(ix.info.len >= (1 << 32))}
     if not os.path.exists(REF_CLASS):
         return {"reads": 0, "identical": None, "tables": tables, "skipped": "oracle/_ref/centrifuge-class not shipped"}
@@ -566,8 +566,8 @@ def _main(result):
     # ---------------- the random-gather ceiling of this device over the replica's own arrays (same process, same footprint)
     ceil = {}
     if "gather" not in a.skip:
-        for name, t in (("rank16", 0), ("ftabk", 1), ("walk8", 2)):
-            have = {"rank16": tb["rank16_bytes"], "ftabk": tb["ftabk_bytes"], "walk8": tb["walk8_bytes"]}[name]
+        for name, t in (("rank16", 0), ("ftabk", 1), ("walk8", 2), ("ftabd", 4)):
+            have = {"rank16": tb["rank16_bytes"], "ftabk": tb["ftabk_bytes"], "walk8": tb["walk8_bytes"], "ftabd": tb["ftabd_bytes"]}[name]
             if have:
                 ceil[name] = capi.gather_ceiling(ix, t, 1 << 31)[0]
         ceil["ftab2"] = None                                  # 16 MB: lives in L2, not a DRAM gather

@@ -29,7 +29,7 @@ class IndexInfo(C.Structure):
 
 class IndexTables(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("sides_bytes", "sample_bytes", "rank16_bytes", "ftab2_bytes", "ftabk_bytes", "resolve_table_bytes",
-                                          "walk8_bytes", "total_bytes", "free_bytes_after_load", "walk8_rows")] + [("ftabk_chars", C.c_int32), ("resolve_entry_bytes", C.c_int32)]
+                                          "walk8_bytes", "total_bytes", "free_bytes_after_load", "walk8_rows", "ftabd_bytes")] + [("ftabk_chars", C.c_int32), ("resolve_entry_bytes", C.c_int32), ("ftabd_chars", C.c_int32), ("pad", C.c_int32)]
 
 
 class Params(C.Structure):
@@ -315,9 +315,9 @@ class Context:
         _ck(lib().cfb_counts_allreduce(arr, C.c_int(1), _p(out, C.c_uint64) if out is not None else None, C.c_uint64(out.size if out is not None else 0)))
 
     def requests(self):
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 5)()
         _ck(lib().cfb_ctx_requests(self.h, out))
-        return dict(zip(["rank16", "ftab2", "ftabk", "walk8"], [int(x) for x in out]))
+        return dict(zip(["rank16", "ftab2", "ftabk", "walk8", "ftabd"], [int(x) for x in out]))
 
     def counters(self):
         out = (C.c_uint64 * 8)()

@@ -180,11 +180,11 @@ extern "C" int cfb_comm_info(const cfb_ctx* c, int* rank, int* size, int* nccl_v
 }
 
 // ------------------------------------------------------------------------------ measurement hooks
-extern "C" int cfb_ctx_requests(cfb_ctx* c, uint64_t out[4]) {
+extern "C" int cfb_ctx_requests(cfb_ctx* c, uint64_t out[5]) {
 	if(!c || !out) return fail(CFB_EINVAL, "null argument");
 	CK(cudaSetDevice(c->ix->device));
 	Counters h; CK(cudaMemcpy(&h, c->d_ctr, sizeof h, cudaMemcpyDeviceToHost));
-	out[0] = h.req_rank16; out[1] = h.req_ftab2; out[2] = h.req_ftabk; out[3] = h.req_walk8;
+	out[0] = h.req_rank16; out[1] = h.req_ftab2; out[2] = h.req_ftabk; out[3] = h.req_walk8; out[4] = h.req_ftabd;
 	return CFB_OK;
 }
 
@@ -219,6 +219,7 @@ extern "C" int cfb_gather_ceiling(const cfb_index* ix, int table, uint64_t n_req
 		case 1: base = (const unsigned long long*)v.ftabk; n = t.ftabk_bytes / 16; W = 2; break;
 		case 2: base = (const unsigned long long*)v.walk8; n = t.walk8_bytes / 8; W = 1; break;
 		case 3: base = v.rtab32 ? (const unsigned long long*)v.rtab32 : (const unsigned long long*)v.rtab16; n = t.resolve_table_bytes / 8; W = 1; break;
+		case 4: base = (const unsigned long long*)v.ftabd; n = t.ftabd_bytes / 8; W = 1; break;
 		default: return fail(CFB_EINVAL, "cfb_gather_ceiling: unknown table %d", table);
 	}
 	if(!base || n == 0) return fail(CFB_EINVAL, "cfb_gather_ceiling: table %d is not built", table);

@@ -22,7 +22,7 @@ using namespace cfb;
 // =======================================================================================
 // k_search
 // =======================================================================================
-enum { M_DONE = 0, M_FTAB = 1, M_LF = 2, M_NEED = 3, M_FTABK = 4 };
+enum { M_DONE = 0, M_FTAB = 1, M_LF = 2, M_NEED = 3, M_FTABK = 4, M_FTABD = 5 };
 
 struct Walk {            // group-uniform state of one greedy strand walk
 	const uint8_t* fw; uint32_t rlen; int strand; uint32_t tid;
@@ -560,7 +560,7 @@ __global__ void k_build_ftab2(IndexView v, uint64_t n, uint64_t* ftab2) {
 static const uint32_t kListNoLong = 0x80000000u;             // flag in nhits[]: the strand has no hit of min_hitlen bases
 static const uint64_t kOccMask = 0x7fffffffffffffffull;
 static const uint64_t kWalkRowMask = (1ull << 40) - 1ull;   // walk8 entry: row in the low 40 bits
-static const int kJumpRows = 1;                             // widest range advanced through walk8.  Ranges of 2-4 adjacent rows can take the same
+static const int kJumpRows __attribute__((unused)) = 1;     // widest range advanced through walk8 (the kernel is specialised for 1).  Ranges of 2-4 adjacent rows can take the same
                                                             // jump (LF keeps them adjacent), but on the bench workload they shrink so often that the
                                                             // failed attempts cost more than the jumps save: 4.44 ms vs 4.25 ms with 1 (measured)
 
@@ -586,6 +586,46 @@ __global__ void k_build_ftabk(IndexView v, int K, uint64_t n, uint64_t* out) {
 	out[fk * 2] = top; out[fk * 2 + 1] = bot;
 }
 
+// Death-depth table: for every (K+3)-mer, how far a partial search that starts with it gets before its SA range empties,
+// as far as that can be said in 2 bits:  1, 2, 3 = the K-mer occurs and the range dies after K, K+1, K+2 bases (the hit
+// partialSearch would report has exactly that length);  0 = the (K+3)-mer occurs, or the K-mer does not (go through the jump
+// table).  A partial search on a strand that does not match -- most searches of most reads -- dies within these three bases
+// and then costs ONE gather instead of the K-mer lookup plus one or two rank gathers per base; its SA range is not
+// computed, which is fine because a hit shorter than min_hitlen is never resolved (k_prep recomputes the range in the
+// rare cases where a short hit's size can influence the result).  Layout: K-mer major, 64 extensions = 16 bytes per K-mer;
+// extension e = c_K | c_{K+1} << 2 | c_{K+2} << 4.  One thread per K-mer walks the depth-3 tree of extensions; a 64-byte
+// rank16 chunk carries the entries of all four bases of a block, so every tree node costs one or two loads.
+__device__ __forceinline__ void lf4(const ulonglong2* r16, const uint64_t* fchr, uint64_t top, uint64_t bot, uint64_t t[4], uint64_t b[4]) {
+	const ulonglong2* pt = r16 + (top >> 6) * 4; const ulonglong2* pb = r16 + (bot >> 6) * 4;
+	const uint64_t mt = (1ull << (top & 63)) - 1ull, mb = (1ull << (bot & 63)) - 1ull;
+	#pragma unroll
+	for(int c = 0; c < 4; c++) {
+		const ulonglong2 et = __ldg(pt + c); const ulonglong2 eb = (pb == pt) ? et : __ldg(pb + c);
+		t[c] = fchr[c] + (et.x & 0x7fffffffffffffffull) + (uint64_t)__popcll(et.y & mt);
+		b[c] = fchr[c] + (eb.x & 0x7fffffffffffffffull) + (uint64_t)__popcll(eb.y & mb);
+	}
+}
+__global__ void __launch_bounds__(128) k_build_ftabd(IndexView v, int K, uint64_t n, uint8_t* out) {
+	const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(f >= n) return;
+	const ulonglong2* r16 = reinterpret_cast<const ulonglong2*>(v.rank16);
+	const uint64_t* base = (K > v.ftab_chars) ? v.ftabk : v.ftab2;
+	const uint64_t top = base[f * 2], bot = base[f * 2 + 1];
+	uint64_t w0 = 0, w1 = 0;                                  // 64 x 2 bits, extension e in bits 2e
+	if(bot > top) {
+		uint64_t t1[4], b1[4]; lf4(r16, v.fchr, top, bot, t1, b1);
+		for(int c0 = 0; c0 < 4; c0++) {
+			if(b1[c0] <= t1[c0]) { for(int r = 0; r < 16; r++) { const int e = c0 | (r << 2); if(e < 32) w0 |= 1ull << (2 * e); else w1 |= 1ull << (2 * (e - 32)); } continue; }
+			uint64_t t2[4], b2[4]; lf4(r16, v.fchr, t1[c0], b1[c0], t2, b2);
+			for(int c1 = 0; c1 < 4; c1++) {
+				if(b2[c1] <= t2[c1]) { for(int c2 = 0; c2 < 4; c2++) { const int e = c0 | (c1 << 2) | (c2 << 4); if(e < 32) w0 |= 2ull << (2 * e); else w1 |= 2ull << (2 * (e - 32)); } continue; }
+				uint64_t t3[4], b3[4]; lf4(r16, v.fchr, t2[c1], b2[c1], t3, b3);
+				for(int c2 = 0; c2 < 4; c2++) if(b3[c2] <= t3[c2]) { const int e = c0 | (c1 << 2) | (c2 << 4); if(e < 32) w0 |= 3ull << (2 * e); else w1 |= 3ull << (2 * (e - 32)); }
+			}
+		}
+	}
+	reinterpret_cast<ulonglong2*>(out)[f] = make_ulonglong2(w0, w1);
+}
 
 struct Blk { uint64_t m[4]; uint32_t pc[4]; };    // match masks of base c and their popcounts
 
@@ -655,13 +695,16 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 	const uint32_t fk = (COUNT == 1 || !a.v.ftabk) ? 0u : (uint32_t)a.v.ftabk_chars;   // counters follow the reference's op sequence
 	const uint32_t fc = (uint32_t)a.v.ftab_chars;
 	const unsigned long long* w8 = COUNT == 1 ? nullptr : reinterpret_cast<const unsigned long long*>(a.v.walk8);
+	// death-depth table: only while every hit it can end (at most fd - 1 bases) stays below min_hitlen, i.e. is never resolved
+	const uint32_t fd = (COUNT == 1 || !a.v.ftabd || a.p.min_hitlen < (uint32_t)a.v.ftabd_chars) ? 0u : (uint32_t)a.v.ftabd_chars;
+	const uint32_t fdk = (uint32_t)a.v.ftabd_base;
 	ReadRegs<RW> rd;
 	uint64_t top = 0, bot = 0, fi = 0;
 	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0, slow_until = 0;
 	bool nolong = true;      // no hit of this strand reaches min_hitlen (kListNoLong tells the per-unit kernels)
 	int mode = M_NEED;
 	unsigned long long c_ps = 0, c_ft = 0, c_sides = 0, c_lf = 0;
-	unsigned long long q_r16 = 0, q_f2 = 0, q_fk = 0, q_w8 = 0;
+	unsigned long long q_r16 = 0, q_f2 = 0, q_fk = 0, q_w8 = 0, q_fd = 0;
 	WarpPool pool; pool.base = pool.end = 0;
 	bool more = true;      // warp-uniform: the global task counter is not exhausted yet
 
@@ -692,6 +735,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 				emit(kOff, kOff, offset, hl);
 				if(after_hit(hl)) continue; else return;
 			}
+			if(fd && rlen - cur >= fd && !(nwin & ((1u << fd) - 1u))) { fi = win & ((1ull << (2 * fd)) - 1ull); mode = M_FTABD; return; }
 			if(fk && rlen - cur >= fk && !(nwin & ((1u << fk) - 1u))) { fi = win & ((1ull << (2 * fk)) - 1ull); mode = M_FTABK; return; }
 			fi = win & ((1ull << (2 * fc)) - 1ull);
 			mode = M_FTAB;
@@ -729,31 +773,55 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 		}
 		if(!__any_sync(0xffffffffu, mode != M_DONE)) break;
 		// ---------------- single fetch point ----------------
+		// Every lane picks the address of the one 16-byte (aligned) piece it needs -- whatever table its walk is at -- plus
+		// a second rank16 entry when a range straddles two 64-row blocks; then ONE predicated load instruction serves all
+		// lanes (and one more the straddlers).  The loads are volatile asm so that the compiler cannot sink each table's
+		// load into the branch that consumes it: it did, and a warp then paid one memory latency per table in play
+		// instead of one per iteration (ncu, profiles/r02: stalls at the K-mer-table consumer with 4 of 32 lanes active).
 		int c = 4;
-		ulonglong2 e = make_ulonglong2(0, 0), tq = e, bq = e;
 		const bool lf = mode == M_LF;
 		bool range = false, jump = false;
-		if(mode == M_FTAB) { e = __ldg(ftab2 + fi); if(COUNT == 2) q_f2++; }                           // (top, bot) of the 10-mer: one request
-		else if(mode == M_FTABK) { e = __ldg(ftabk + fi); if(COUNT == 2) q_fk++; }                     // (top, bot) of the K-mer
+		const void* p0 = nullptr; const void* p1 = nullptr; uint32_t sub = 0;
+		if(mode == M_FTABD) {                                                // 2 bits of the death-depth table
+			const uint64_t idx = ((fi & ((1ull << (2 * fdk)) - 1ull)) << 6) | (fi >> (2 * fdk));
+			const uint64_t byte = idx >> 2;
+			p0 = a.v.ftabd + (byte & ~15ull); sub = (uint32_t)(byte & 15) * 8u + (uint32_t)(idx & 3) * 2u;
+			if(COUNT == 2) q_fd++;
+		}
+		else if(mode == M_FTAB) { p0 = ftab2 + fi; if(COUNT == 2) q_f2++; }                           // (top, bot) of the 10-mer
+		else if(mode == M_FTABK) { p0 = ftabk + fi; if(COUNT == 2) q_fk++; }                          // (top, bot) of the K-mer
 		else if(lf) {
 			c = rd.base(dep);
 			if(c <= 3) {
 				range = (bot - top) != 1;
-				if(w8 && (bot - top) <= (uint64_t)kJumpRows && dep >= slow_until && rlen - dep >= 8 && bot <= a.v.walk8_rows) {
-					// eight steps in one gather: a single row, or a narrow range whose rows (consecutive walk8 entries, one
-					// or two sectors) all continue with the read's next eight bases -- LF keeps such rows adjacent
-					jump = true; e.x = __ldg(w8 + top); e.y = 0; if(COUNT == 2) q_w8++;
-					#pragma unroll
-					for(int i = 1; i < kJumpRows; i++) if(top + i < bot) { const unsigned long long o = __ldg(w8 + top + i); e.y |= (o ^ e.x) >> 40; }   // bases + count must equal entry 0's
+				if(w8 && !range && dep >= slow_until && rlen - dep >= 8 && bot <= a.v.walk8_rows) {
+					// eight steps in one gather while the walk holds a single row and the read's next eight bases are the stored ones
+					jump = true; p0 = w8 + (top & ~1ull); sub = (uint32_t)(top & 1); if(COUNT == 2) q_w8++;
 				} else {
-					tq = __ldg(r16 + (top >> 6) * 4 + c);                   // (occ, bits): one request per rank query
-					bq = tq; if(COUNT == 2) q_r16++;
-					if(range && (bot >> 6) != (top >> 6)) { bq = __ldg(r16 + (bot >> 6) * 4 + c); if(COUNT == 2) q_r16++; }
+					p0 = r16 + (top >> 6) * 4 + c;                          // (occ, bits): one request per rank query
+					if(COUNT == 2) q_r16++;
+					if(range && (bot >> 6) != (top >> 6)) { p1 = r16 + (bot >> 6) * 4 + c; if(COUNT == 2) q_r16++; }
 				}
 			}
 		}
+		ulonglong2 e = make_ulonglong2(0, 0), bq;
+		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u64 p, %2, 0;\n\t@p ld.global.nc.v2.u64 {%0, %1}, [%2];\n\t}" : "+l"(e.x), "+l"(e.y) : "l"(p0));
+		bq = e;
+		asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u64 p, %2, 0;\n\t@p ld.global.nc.v2.u64 {%0, %1}, [%2];\n\t}" : "+l"(bq.x), "+l"(bq.y) : "l"(p1));
+		const ulonglong2 tq = e;
 		// ---------------- consume ----------------
-		if(mode == M_FTABK) {
+		if(mode == M_FTABD) {
+			const uint32_t dv = (uint32_t)(((sub & 64u) ? e.y : e.x) >> (sub & 63u)) & 3u;
+			if(dv == 0) {                                 // the (K+3)-mer occurs (or the K-mer does not): through the jump table
+				fi &= (1ull << (2 * fdk)) - 1ull;
+				mode = (fk && fdk == fk) ? M_FTABK : M_FTAB;
+			} else {                                      // the range dies after K + v - 1 bases: that is the hit partialSearch reports
+				const uint32_t hl = fdk + dv - 1u;
+				emit(kUnk, kUnk, offset, hl);
+				cur += hl;
+				if(after_hit(hl)) start_search();
+			}
+		} else if(mode == M_FTABK) {
 			if(e.y > e.x) {                               // same state partialSearch reaches after K bases
 				top = e.x; bot = e.y; dep = cur + fk;
 				if(dep < rlen) mode = M_LF; else hit_and_restart();
@@ -771,9 +839,9 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 			else hit_and_restart();
 		} else if(jump) {
 			uint64_t win; uint32_t nwin; rd.window(dep, win, nwin);
-			if((e.x >> 56) == 8 && !e.y && !(nwin & 0xffu) && !(((e.x >> 40) ^ win) & 0xffffull)) {
-				const uint64_t rows = bot - top;
-				top = e.x & kWalkRowMask; bot = top + rows; dep += 8;
+			const uint64_t w = sub ? e.y : e.x;
+			if((w >> 56) == 8 && !(nwin & 0xffu) && !(((w >> 40) ^ win) & 0xffffull)) {
+				top = w & kWalkRowMask; bot = top + 1; dep += 8;
 				if(dep >= rlen) hit_and_restart();
 			} else slow_until = dep + 8;                 // one of the next eight steps ends the hit: take them one by one
 		} else if(lf) {
@@ -803,7 +871,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 		atomicAdd(&a.ctr->sides_search, c_sides); atomicAdd(&a.ctr->lf_steps, c_lf);
 	}
 	if(COUNT == 2 && a.ctr) {
-		atomicAdd(&a.ctr->req_rank16, q_r16); atomicAdd(&a.ctr->req_ftab2, q_f2); atomicAdd(&a.ctr->req_ftabk, q_fk); atomicAdd(&a.ctr->req_walk8, q_w8);
+		atomicAdd(&a.ctr->req_rank16, q_r16); atomicAdd(&a.ctr->req_ftab2, q_f2); atomicAdd(&a.ctr->req_ftabk, q_fk); atomicAdd(&a.ctr->req_walk8, q_w8); atomicAdd(&a.ctr->req_ftabd, q_fd);
 	}
 }
 
@@ -872,6 +940,22 @@ __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
 		else {
 			Counters local; Counters* lc = nullptr;
 			if(a.ctr) { memset(&local, 0, sizeof local); lc = &local; }
+			// Hits the death-depth table ended carry no SA range.  A short hit's range can matter only through the twin
+			// removal (both strands in play, classifier.h:850-870) or through libstdc++'s tie permutation in lists long
+			// enough for introsort (> 16 hits): recompute the ranges there, exactly as partialSearch would.
+			for(int r = 0; r < u.n_mates; r++) {
+				const bool both = u.n[r][0] > 0 && u.n[r][1] > 0;
+				for(int st = 0; st < 2; st++) {
+					if(!both && u.n[r][st] <= 16) continue;
+					for(uint32_t i = 0; i < u.n[r][st]; i++) {
+						HitRec& h = u.L[r][st][i];
+						if(h.top != kUnk) continue;
+						HitRec t; uint32_t nc; bool dn;
+						partial_search_scalar(a.v, fw[r], u.rdlen[r], st, h.bwoff, t, nc, dn, nullptr);
+						h.top = t.top; h.bot = t.bot;
+					}
+				}
+			}
 			for(int r = 0; r < u.n_mates; r++) post_search(a.v, a.p, fw[r], u.rdlen[r], u.L[r][0], u.n[r][0], u.L[r][1], u.n[r][1], lc);
 			SortAndCount sc(a.p, u);
 			for_each_visit(a.p, u, sc);
@@ -899,6 +983,7 @@ __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
 	if(rows && off + rows <= a.rows_cap) { EmitRows er(a.p, u, a.rows + off); for_each_visit(a.p, u, er); }   // else: the host grows the buffer and re-runs EMIT_ONLY
 }
 
+static const int kLocalMap = 4;
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_score(const UnitArgs a) {
 	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
@@ -909,8 +994,13 @@ __global__ void __launch_bounds__(128, MINB) k_score(const UnitArgs a) {
 		const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
 		int mates = 0;
 		for(int m = 0; m < a.b.n_mates; m++) if(((fl >> m) & 1) && (m ? a.b.len[1][unit] : a.b.len[0][unit]) != 0) mates++;
-		const uint32_t nmap = score_plan(a.v, a.p, a.rows + off, a.ids + off, n, a.entries + off);
-		no = reduce_and_emit(a.v, a.p, mates == 2, a.entries + off, nmap, a.tcs + off, a.recs_sparse + off);
+		// the hit map of a unit with a handful of rows lives in thread-local memory (interleaved across the warp, L1-resident)
+		// instead of the per-unit slice of the global scratch, whose 72-byte entries of neighbouring threads never share a sector
+		Entry lmap[kLocalMap]; TaxCnt ltc[kLocalMap];
+		Entry* map = n <= (uint64_t)kLocalMap ? lmap : a.entries + off;
+		TaxCnt* tc = n <= (uint64_t)kLocalMap ? ltc : a.tcs + off;
+		const uint32_t nmap = score_plan(a.v, a.p, a.rows + off, a.ids + off, n, map);
+		no = reduce_and_emit(a.v, a.p, mates == 2, map, nmap, tc, a.recs_sparse + off);
 	}
 	a.nout[unit] = no;
 }
@@ -1432,7 +1522,7 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 			}
 			// HBM budget of the derived tables: what is free now minus the head-room the batch buffers need (24 GB by default:
 			// 16 slots of 0.5 M reads at ~3.5 KB each; CFB_HBM_HEADROOM_GB).  Tables are built in the order of gathers saved per
-			// byte -- K-mer jump table, resolve table, walk8 -- each only if it fits what is left; walk8, whose rows are hit
+			// byte -- K-mer jump table, resolve table, death-depth table, walk8 -- each only if it fits what is left; walk8, whose rows are hit
 			// uniformly, may cover just a prefix of the rows (a jump needs an entry for the row it starts from only).
 			size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
 			double head_gb = 24.0; { const char* e = getenv("CFB_HBM_HEADROOM_GB"); if(e) head_gb = atof(e); }
@@ -1469,6 +1559,22 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 					cudaFree(sc);
 					if(h.wide_sample) v.rtab32 = (const uint32_t*)tab; else v.rtab16 = (const uint16_t*)tab;
 					ix->tables.resolve_table_bytes = nrows * esz; ix->tables.resolve_entry_bytes = (int32_t)esz;
+				}
+			}
+			// death-depth table over the (K+3)-mers of the jump table in use (the K-mer table, else the 10-mer table): same
+			// size as a K-mer table of that K (16 bytes per K-mer)
+			{
+				const char* e = getenv("CFB_FTABD");
+				const int Kb = v.ftabk ? v.ftabk_chars : h.ftab_chars;
+				const uint64_t nk = 1ull << (2 * Kb);
+				if(!(e && e[0] == '0') && Kb + 3 <= 20 && nk * 16 <= budget()) {
+					uint8_t* fd = nullptr;
+					CK(cudaMalloc((void**)&fd, nk * 16));
+					ix->dptrs.push_back(fd); ix->device_bytes += nk * 16;
+					k_build_ftabd<<<(unsigned)((nk + 127) / 128), 128>>>(v, Kb, nk, fd);
+					CK(cudaDeviceSynchronize());
+					v.ftabd = fd; v.ftabd_chars = Kb + 3; v.ftabd_base = Kb;
+					ix->tables.ftabd_bytes = nk * 16; ix->tables.ftabd_chars = Kb + 3;
 				}
 			}
 			// walk8: eight single-row LF steps per gather, for as many rows as the budget allows (at least an eighth of them)

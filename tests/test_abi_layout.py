@@ -21,7 +21,10 @@ int main(void) {
   S(cfb_result); F(cfb_result, rec_off); F(cfb_result, recs);
   S(cfb_text_opts); F(cfb_text_opts, maxlen_hint);
   S(cfb_text_result); F(cfb_text_result, tsv); F(cfb_text_result, multi); F(cfb_text_result, multi_stride);
-  S(cfb_build_opts); F(cfb_build_opts, synth_len); F(cfb_build_opts, synth_div); F(cfb_build_opts, ftab_chars); F(cfb_build_opts, verbose);
+  S(cfb_build_opts); F(cfb_build_opts, synth_len); F(cfb_build_opts, synth_div); F(cfb_build_opts, ftab_chars); F(cfb_build_opts, verbose); F(cfb_build_opts, synth_prefix);
+  S(cfb_index_tables); F(cfb_index_tables, walk8_bytes); F(cfb_index_tables, walk8_rows); F(cfb_index_tables, ftabd_bytes); F(cfb_index_tables, ftabk_chars); F(cfb_index_tables, ftabd_chars);
+  S(cfb_batch_packed); F(cfb_batch_packed, words); F(cfb_batch_packed, len); F(cfb_batch_packed, n_pos); F(cfb_batch_packed, flags);
+  S(cfb_synth_read_opts); F(cfb_synth_read_opts, paired); F(cfb_synth_read_opts, ins_hi);
   return 0;
 }
 """
@@ -40,7 +43,8 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     import numpy as np
     rec = np.dtype([("taxid", "<u8"), ("score", "<u4"), ("hitlen", "<u4"), ("uid", "<u4"), ("pad", "<u4")])
     pairs = {"cfb_index_info": capi.IndexInfo, "cfb_params": capi.Params, "cfb_batch": capi.BatchC, "cfb_result": capi.ResultC,
-             "cfb_text_opts": capi.TextOpts, "cfb_text_result": capi.TextResultC, "cfb_build_opts": capi.BuildOpts}
+             "cfb_text_opts": capi.TextOpts, "cfb_text_result": capi.TextResultC, "cfb_build_opts": capi.BuildOpts,
+             "cfb_index_tables": capi.IndexTables, "cfb_batch_packed": capi.BatchPackedC, "cfb_synth_read_opts": capi.SynthReadOpts}
     for cname, st in pairs.items():
         assert got[cname + ".size"] == C.sizeof(st), cname
         for key, off in got.items():

@@ -121,13 +121,17 @@ def test_bench_data_path_matches_reference_end_to_end(tmp_path):
     tax = m.write_synth_taxonomy(d, g, s, L)
     o = m.build_opts(d + "/idx", synth=(g, s, L, 4242, 0.03), conversion_table=tax[0], taxonomy_tree=tax[1], name_table=tax[2])
     m.build_index(o)
-    codes = m.synth_reads(o, 30000, 100, 17)
-    fq = d + "/r.fq"
-    bench.write_fastq(fq, codes)
     exe = os.path.join(util.ROOT, "centrifuge_b200", "centrifuge-class")
-    a = util.run_cli(util.REF_CLASS, ["-q", "-x", d + "/idx", "-U", fq], d + "/a.tsv", d + "/a.rep")
-    b = util.run_cli(exe, ["-q", "-x", d + "/idx", "-U", fq, "--batch-units", "7000"], d + "/b.tsv", d + "/b.rep")
-    assert a[0] == b[0]
-    assert a[1] == b[1]
-    rows = a[0].decode().strip().split("\n")[1:]
-    assert sum(1 for r in rows if "unclassified" not in r) > 25000      # the synthetic reads do classify
+    # bench.py's three workloads: fixed-length SE, mixed-length SE, paired (its own generator and FASTQ writer)
+    for tag, lens, paired in (("se", (100, 100), False), ("mixed", (75, 300), False), ("pe", (150, 150), True)):
+        codes, ln = m.synth_reads_ex(o, 20000, 17, lens[0], lens[1], paired=paired)
+        rd = bench.Reads(codes, ln)
+        files = [d + "/%s_%d.fq" % (tag, k + 1) for k in range(rd.mates)]
+        bench.write_fastq_files(rd, files)
+        rargs = ["-q", "-x", d + "/idx"] + (["-1", files[0], "-2", files[1]] if paired else ["-U", files[0]])
+        a = util.run_cli(util.REF_CLASS, rargs, d + "/a.tsv", d + "/a.rep")
+        b = util.run_cli(exe, rargs + ["--batch-units", "7000"], d + "/b.tsv", d + "/b.rep")
+        assert a[0] == b[0], tag
+        assert a[1] == b[1], tag
+        rows = a[0].decode().strip().split("\n")[1:]
+        assert sum(1 for r in rows if "unclassified" not in r) > 15000, tag      # the synthetic reads do classify

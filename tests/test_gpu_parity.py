@@ -90,7 +90,10 @@ def test_classify_matches_oracle_adversarial(case, adv_base, adv_reads):
 
 LAYOUT_VARIANTS = {
     "no_walk8": {"CFB_WALK8": "0"},
-    "no_tables": {"CFB_WALK8": "0", "CFB_RESOLVE_TABLE": "0", "CFB_FTABK": "10"},
+    "no_ftabd": {"CFB_FTABD": "0"},
+    "ftabd_over_ftabk12": {"CFB_FTABK": "12"},
+    "half_walk8": {"CFB_WALK8_ROWS": "300000"},
+    "no_tables": {"CFB_WALK8": "0", "CFB_RESOLVE_TABLE": "0", "CFB_FTABK": "10", "CFB_FTABD": "0"},
     "ftabk11": {"CFB_FTABK": "11"},
     "ftabk12_walk_resolve": {"CFB_FTABK": "12", "CFB_RESOLVE_TABLE": "0"},
     "coop8": {"CFB_GROUP": "8", "CFB_LEGACY_LAYOUTS": "1"},
