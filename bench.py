@@ -608,14 +608,17 @@ def _main(result):
     # ---------------- e2e arms: host buffers in, host results out, sub-batches streaming over the context's slots
     nslots = min(ctx.n_slots, E2E_SLOTS)
 
+    host_s = {"submit": 0.0, "wait": 0.0}
+
     def stream(steps, submit, wait, per_step):
         got, q, pending = 0, 0, [None] * nslots
         for st in range(steps):
             for i in range(nsub):
                 sl = q % nslots; q += 1
                 if pending[sl] is not None:
-                    got += wait(sl)
-                submit(sl, i); pending[sl] = i
+                    t_ = time.perf_counter(); got += wait(sl); host_s["wait"] += time.perf_counter() - t_
+                t_ = time.perf_counter(); submit(sl, i); host_s["submit"] += time.perf_counter() - t_
+                pending[sl] = i
             if per_step:
                 per_step()
         for k in range(nslots):                                  # drain in submission order
@@ -630,19 +633,20 @@ def _main(result):
         run = lambda steps: stream(steps, lambda sl, i: submit_fn(sl, forms[i]), lambda sl: ctx.wait(sl, copy=False)[1], ctx.counts_allreduce)   # noqa: E731
         run(max(1, min(a.warmup, 2)))                             # every slot allocates its buffers before the timed region
         ctx.counts_reset()
+        host_s["submit"] = host_s["wait"] = 0.0
         nrec, ds, ws = timed(lambda: run(a.steps))
-        return world * n * a.steps / ds, nrec, ds, ws
+        return world * n * a.steps / ds, nrec, ds, ws, {k: 1000 * v / a.steps for k, v in host_s.items()}
 
-    e2e, nrec_e2e, e2e_dev_s, e2e_wall_s = e2e_arm(packed, ctx.submit_packed)
+    e2e, nrec_e2e, e2e_dev_s, e2e_wall_s, e2e_host = e2e_arm(packed, ctx.submit_packed)
     d2h = nrec_e2e * 24 // a.steps + (n + nsub) * 4
     e2e_counts = int(ctx.counts_dense(global_=True, n=n_tax)[0].sum())
     out_e2e = {"value": e2e, "unit": unit, "h2d_bytes_per_step": int(h2d_packed), "d2h_bytes_per_step": int(d2h),
                "what": "cfb_classify_submit_packed/wait: 2-bit packed reads + lengths + N list in pinned host memory -> result records in host memory; %d sub-batches of %d units per step streaming over %d slots; per-taxon counters folded on the device and all-reduced once per step" % (nsub, a.sub, nslots),
-               "assignments_counted_global": e2e_counts}
+               "assignments_counted_global": e2e_counts, "host_ms_per_step_in_calls": e2e_host}
     out_bf = None
     if "e2e_byteform" not in a.skip:
-        v, nr, _, _ = e2e_arm(byteform, ctx.submit)
-        out_bf = {"value": v, "unit": unit, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(nr * 24 // a.steps + (n + nsub) * 4),
+        v, nr, _, _, bf_host = e2e_arm(byteform, ctx.submit)
+        out_bf = {"value": v, "unit": unit, "host_ms_per_step_in_calls": bf_host, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(nr * 24 // a.steps + (n + nsub) * 4),
                   "what": "cfb_classify_submit/wait with the 1-byte-per-base cfb_batch form"}
     out_text = None
     if "e2e_text" not in a.skip:
