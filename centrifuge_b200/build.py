@@ -17,7 +17,7 @@ CLI = os.path.join(HERE, "centrifuge-class")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-Wno-deprecated-declarations", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-Wno-deprecated-declarations,-ffp-contract=off", "--expt-relaxed-constexpr",
     "-Wno-deprecated-gpu-targets", "-diag-suppress", "1444",
 ]
 

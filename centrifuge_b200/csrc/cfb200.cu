@@ -1452,6 +1452,8 @@ static int stream_to_device(cfb_index* ix, const std::string& path, uint64_t off
 	return rc;
 }
 
+// CK inside the loader: the half-built replica is released before the error is returned
+#define CKX(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { const int rc_ = fail(CFB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); cfb_index_free(ix); return rc_; } } while(0)
 extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flags, cfb_index** out) {
 	if(!basename || !out) return fail(CFB_EINVAL, "cfb_index_load: null argument");
 	cfb_index* ix = new cfb_index();
@@ -1485,31 +1487,31 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 		v.off_rate = h.off_rate; v.ftab_chars = h.ftab_chars; v.bshift = h.bshift;
 		if(getenv("CFB_LEGACY_LAYOUTS")) {   // 64-byte blocks: only for the k_resolve_t A/B variant (CFB_RESOLVE=1)
 			uint64_t* blk = nullptr; const uint64_t nb = h.num_sides * 3;
-			CK(cudaMalloc((void**)&blk, (nb + 1) * 64));
+			CKX(cudaMalloc((void**)&blk, (nb + 1) * 64));
 			ix->dptrs.push_back(blk); ix->device_bytes += (nb + 1) * 64;
 			k_build_blocks<<<(unsigned)((nb + 1 + 255) / 256), 256>>>(v.sides, h.num_sides, v.zside, v.zoffc, blk);
-			CK(cudaDeviceSynchronize());
+			CKX(cudaDeviceSynchronize());
 			v.blocks = blk; v.num_blocks = nb;
 		}
 		if(getenv("CFB_LEGACY_LAYOUTS")) {   // 32-byte rank sectors: superseded by rank16, kept for A/B only
 			uint64_t* rv = nullptr; const uint64_t nb = h.num_sides * 2;
-			CK(cudaMalloc((void**)&rv, (nb + 1) * 128));
+			CKX(cudaMalloc((void**)&rv, (nb + 1) * 128));
 			ix->dptrs.push_back(rv); ix->device_bytes += (nb + 1) * 128;
 			k_build_rankv<<<(unsigned)((nb + 1 + 255) / 256), 256>>>(v.sides, h.num_sides, v.zside, v.zoffc, rv);
-			CK(cudaDeviceSynchronize());
+			CKX(cudaDeviceSynchronize());
 			v.rankv = rv;
 		}
 		{   // 16-byte rank entries + fused ftab for the walk kernels
 			uint64_t* r16 = nullptr; const uint64_t nb = h.num_sides * 6;
-			CK(cudaMalloc((void**)&r16, (nb + 1) * 64));
+			CKX(cudaMalloc((void**)&r16, (nb + 1) * 64));
 			ix->dptrs.push_back(r16); ix->device_bytes += (nb + 1) * 64;
 			k_build_rank16<<<(unsigned)((nb + 1 + 255) / 256), 256>>>(v.sides, h.num_sides, v.zside, v.zoffc, r16);
 			if(v.n_boundaries) k_mark_boundaries<<<(v.n_boundaries + 255) / 256, 256>>>(v.brow, v.n_boundaries, r16);
 			uint64_t* f2 = nullptr; const uint64_t nf = h.ftab_len - 1;
-			CK(cudaMalloc((void**)&f2, nf * 16));
+			CKX(cudaMalloc((void**)&f2, nf * 16));
 			ix->dptrs.push_back(f2); ix->device_bytes += nf * 16;
 			k_build_ftab2<<<(unsigned)((nf + 255) / 256), 256>>>(v, nf, f2);
-			CK(cudaDeviceSynchronize());
+			CKX(cudaDeviceSynchronize());
 			v.rank16 = r16; v.ftab2 = f2;
 			ix->tables.rank16_bytes = (nb + 1) * 64; ix->tables.ftab2_bytes = nf * 16;
 			// The file's sides have served their purpose (rank16 holds the same information, and the rare scalar LF of the
@@ -1534,10 +1536,10 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 			while(K > h.ftab_chars && (16ull << (2 * K)) > budget() / 2) K--;
 			if(K > h.ftab_chars && K <= 16) {
 				uint64_t* fk = nullptr; const uint64_t nk = 1ull << (2 * K);
-				CK(cudaMalloc((void**)&fk, nk * 16));
+				CKX(cudaMalloc((void**)&fk, nk * 16));
 				ix->dptrs.push_back(fk); ix->device_bytes += nk * 16;
 				k_build_ftabk<<<(unsigned)((nk + 255) / 256), 256>>>(v, K, nk, fk);
-				CK(cudaDeviceSynchronize());
+				CKX(cudaDeviceSynchronize());
 				v.ftabk = fk; v.ftabk_chars = K;
 				ix->tables.ftabk_bytes = nk * 16; ix->tables.ftabk_chars = K;
 			}
@@ -1547,15 +1549,15 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 				const uint64_t nrows = h.len + 1, esz = h.wide_sample ? 4 : 2;
 				if(!(e && e[0] == '0') && nrows * esz + 16 <= budget()) {
 					void* tab = nullptr; unsigned long long* sc = nullptr;
-					CK(cudaMalloc(&tab, nrows * esz + 16)); CK(cudaMalloc((void**)&sc, 16));
+					CKX(cudaMalloc(&tab, nrows * esz + 16)); CKX(cudaMalloc((void**)&sc, 16));
 					ix->dptrs.push_back(tab); ix->device_bytes += nrows * esz;
 					const unsigned long long init[2] = {0ull, (unsigned long long)nrows};
-					CK(cudaMemcpy(sc, init, 16, cudaMemcpyHostToDevice));
+					CKX(cudaMemcpy(sc, init, 16, cudaMemcpyHostToDevice));
 					ResolveArgs ra; ra.v = v; ra.rows = nullptr; ra.ids = h.wide_sample ? (uint32_t*)tab : nullptr; ra.ids16 = h.wide_sample ? nullptr : (uint16_t*)tab;
 					ra.total = (const uint64_t*)(sc + 1); ra.rows_cap = nrows; ra.task_ctr = sc; ra.chunk = 256; ra.ctr = nullptr;
 					int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_c<false, true>, kSearchThreads, 0);
 					k_resolve_c<false, true><<<prop.multiProcessorCount * std::max(occ, 1), kSearchThreads>>>(ra);
-					CK(cudaDeviceSynchronize());
+					CKX(cudaDeviceSynchronize());
 					cudaFree(sc);
 					if(h.wide_sample) v.rtab32 = (const uint32_t*)tab; else v.rtab16 = (const uint16_t*)tab;
 					ix->tables.resolve_table_bytes = nrows * esz; ix->tables.resolve_entry_bytes = (int32_t)esz;
@@ -1569,10 +1571,10 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 				const uint64_t nk = 1ull << (2 * Kb);
 				if(!(e && e[0] == '0') && Kb + 3 <= 20 && nk * 16 <= budget()) {
 					uint8_t* fd = nullptr;
-					CK(cudaMalloc((void**)&fd, nk * 16));
+					CKX(cudaMalloc((void**)&fd, nk * 16));
 					ix->dptrs.push_back(fd); ix->device_bytes += nk * 16;
 					k_build_ftabd<<<(unsigned)((nk + 127) / 128), 128>>>(v, Kb, nk, fd);
-					CK(cudaDeviceSynchronize());
+					CKX(cudaDeviceSynchronize());
 					v.ftabd = fd; v.ftabd_chars = Kb + 3; v.ftabd_base = Kb;
 					ix->tables.ftabd_bytes = nk * 16; ix->tables.ftabd_chars = Kb + 3;
 				}
@@ -1585,11 +1587,11 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 				{ const char* f = getenv("CFB_WALK8_ROWS"); if(f) cover = std::min<uint64_t>(nrows, strtoull(f, NULL, 10)); }     // tests: force a partial table
 				if(!(e && e[0] == '0') && nrows < (1ull << 40) && cover >= nrows / 8 && cover > 0) {
 					void* tab = nullptr;
-					CK(cudaMalloc(&tab, cover * 8 + 16));
+					CKX(cudaMalloc(&tab, cover * 8 + 16));
 					ix->dptrs.push_back(tab); ix->device_bytes += cover * 8;
 					int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_build_walk8, kSearchThreads, 0);
 					k_build_walk8<<<prop.multiProcessorCount * std::max(occ, 1) * 4, kSearchThreads>>>(v, cover, (uint64_t*)tab);
-					CK(cudaDeviceSynchronize());
+					CKX(cudaDeviceSynchronize());
 					v.walk8 = (const uint64_t*)tab; v.walk8_rows = cover;
 					ix->tables.walk8_bytes = cover * 8; ix->tables.walk8_rows = cover;
 				}
@@ -1602,6 +1604,7 @@ extern "C" int cfb_index_load_ex(const char* basename, int device, uint32_t flag
 	*out = ix;
 	return CFB_OK;
 }
+#undef CKX
 extern "C" int cfb_index_load(const char* basename, int device, cfb_index** out) { return cfb_index_load_ex(basename, device, 0u, out); }
 extern "C" void cfb_index_free(cfb_index* ix) {
 	if(!ix) return;

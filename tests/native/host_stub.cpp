@@ -1,7 +1,7 @@
 // tests/native/host_stub.cpp -- TEST ONLY.  Lets the host side of the product (centrifuge_b200/csrc/cf_host.cpp +
 // cf_index.cpp) link without the CUDA translation units, so that its CPU-testable entry points (cfb_test_parse,
 // cfb_test_host_path, cfb_kreport, cfb_em_abundance_host) can be run under ASan / UBSan:
-//   g++ -O1 -g -std=c++17 -fsanitize=address,undefined -shared -fPIC -o /tmp/libcfbhost_san.so \
+//   g++ -O1 -g -std=c++17 -ffp-contract=off -fsanitize=address,undefined -shared -fPIC -o /tmp/libcfbhost_san.so \
 //       tests/native/host_stub.cpp centrifuge_b200/csrc/cf_host.cpp centrifuge_b200/csrc/cf_index.cpp -lpthread
 //   LD_PRELOAD=$(gcc -print-file-name=libasan.so):$(gcc -print-file-name=libubsan.so) ASAN_OPTIONS=detect_leaks=0 \
 //       CFB_PRODUCT_LIB=/tmp/libcfbhost_san.so python -m pytest tests/test_reader_fuzz.py tests/test_host_path.py tests/test_kreport.py tests/test_em_host.py -m "not gpu"

@@ -32,6 +32,7 @@ extern "C" void* hl_load(const char* base, char* err, size_t errlen) {
 	HL* x = new HL();
 	std::string e = load_cf_index(base, x->h);
 	if(!e.empty()) { strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; delete x; return NULL; }
+	if(x->h.line_rate != 7) { strncpy(err, "the scalar logic (like the kernels) assumes 128-byte sides: lineRate 7 only", errlen - 1); err[errlen - 1] = 0; delete x; return NULL; }
 	const HostIndex& h = x->h; IndexView& v = x->v; memset(&v, 0, sizeof v);
 	v.sides = (const uint64_t*)h.sides.data(); v.ftab = h.ftab.data(); v.eftab = h.eftab.data();
 	v.sample16 = h.wide_sample ? NULL : h.sample16.data(); v.sample32 = h.wide_sample ? h.sample32.data() : NULL;

@@ -46,7 +46,7 @@ def ensure_oracle():
             os.path.join(ROOT, "centrifuge_b200", "csrc", "cf_logic.h")]
     if not os.path.exists(HOSTLOGIC_LIB) or any(os.path.getmtime(s) > os.path.getmtime(HOSTLOGIC_LIB) for s in srcs):
         os.makedirs(REFDIR, exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", HOSTLOGIC_LIB, srcs[0], srcs[1]])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", HOSTLOGIC_LIB, srcs[0], srcs[1]])
 
 
 # ----------------------------------------------------------------------------- fixtures
