@@ -39,6 +39,7 @@ struct SearchArgs {
 	unsigned int* overflow;
 	Counters* ctr;
 	const uint64_t* pk; const uint32_t* nm; uint32_t W;   // packed reads (k_pack)
+	uint32_t jump_w;                                      // widest range advanced eight bases per gather through walk8 (CFB_JUMP_W)
 };
 
 // row -> (side, offset in side).  Rows are < 2^39 for any index that fits in HBM, so row>>7 fits
@@ -700,7 +701,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 	const uint32_t fdk = (uint32_t)a.v.ftabd_base;
 	ReadRegs<RW> rd;
 	uint64_t top = 0, bot = 0, fi = 0;
-	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0, slow_until = 0;
+	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0, slow_until = 0, fail_w = 0;
 	bool nolong = true;      // no hit of this strand reaches min_hitlen (kListNoLong tells the per-unit kernels)
 	int mode = M_NEED;
 	unsigned long long c_ps = 0, c_ft = 0, c_sides = 0, c_lf = 0;
@@ -765,7 +766,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 						const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
 						nh = 0; rlen = a.b.len[mate][unit];
 						if(!((fl >> mate) & 1) || rlen == 0) a.nhits[tid] = 0;          // filtered mate: stays M_NEED
-						else { rd.load(a.pk + (size_t)tid * a.W, a.nm + (size_t)tid * a.W, a.W); cur = 0; slow_until = 0; nolong = true; start_search(); }
+						else { rd.load(a.pk + (size_t)tid * a.W, a.nm + (size_t)tid * a.W, a.W); cur = 0; slow_until = 0; fail_w = 0; nolong = true; start_search(); }
 					} else mode = M_DONE;
 				}
 				if(__any_sync(0xffffffffu, want && !got)) more = false;      // global counter ran past the end
@@ -794,9 +795,14 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 			c = rd.base(dep);
 			if(c <= 3) {
 				range = (bot - top) != 1;
-				if(w8 && !range && dep >= slow_until && rlen - dep >= 8 && bot <= a.v.walk8_rows) {
-					// eight steps in one gather while the walk holds a single row and the read's next eight bases are the stored ones
+				const uint64_t width = bot - top;
+				if(w8 && width <= (uint64_t)a.jump_w && (dep >= slow_until || width < (uint64_t)fail_w) && rlen - dep >= 8 && bot <= a.v.walk8_rows) {
+					// Eight steps in one gather: while the walk holds a single row -- or a narrow range -- and the read's next eight
+					// bases are the ones stored for its first AND its last row.  LF keeps the order of rows that continue with the
+					// same base, so the range survives the eight steps intact exactly when both end rows do and their images are
+					// still width - 1 apart (every row that drops out in between shortens that distance by one, nothing widens it).
 					jump = true; p0 = w8 + (top & ~1ull); sub = (uint32_t)(top & 1); if(COUNT == 2) q_w8++;
+					if(range) { const uint64_t last = bot - 1; sub |= (uint32_t)(last & 1) << 1; if((last & ~1ull) != (top & ~1ull)) { p1 = w8 + (last & ~1ull); if(COUNT == 2) q_w8++; } }
 				} else {
 					p0 = r16 + (top >> 6) * 4 + c;                          // (occ, bits): one request per rank query
 					if(COUNT == 2) q_r16++;
@@ -839,11 +845,14 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 			else hit_and_restart();
 		} else if(jump) {
 			uint64_t win; uint32_t nwin; rd.window(dep, win, nwin);
-			const uint64_t w = sub ? e.y : e.x;
-			if((w >> 56) == 8 && !(nwin & 0xffu) && !(((w >> 40) ^ win) & 0xffffull)) {
-				top = w & kWalkRowMask; bot = top + 1; dep += 8;
+			const uint64_t w = (sub & 1u) ? e.y : e.x;                       // entry of the first row
+			const uint64_t wl = (sub & 2u) ? bq.y : bq.x;                    // entry of the last row (the same entry for a single row)
+			const uint64_t width = bot - top;
+			if((w >> 56) == 8 && !(nwin & 0xffu) && !(((w >> 40) ^ win) & 0xffffull)
+			   && (width == 1 || ((wl >> 40) == (w >> 40) && (wl & kWalkRowMask) - (w & kWalkRowMask) == width - 1))) {
+				top = w & kWalkRowMask; bot = top + width; dep += 8;
 				if(dep >= rlen) hit_and_restart();
-			} else slow_until = dep + 8;                 // one of the next eight steps ends the hit: take them one by one
+			} else { slow_until = dep + 8; fail_w = (uint32_t)width; }   // some row leaves within the next eight steps: take them one by one (a narrower range may try again)
 		} else if(lf) {
 			bool fail = c > 3;
 			uint64_t t = 0, b = 0;
@@ -1708,6 +1717,7 @@ struct cfb_ctx {
 	uint64_t rows_cap0 = 0;       // CFB_ROWS_CAP: initial row-buffer capacity (tests force the grow-and-re-run path with it)
 	TextCtx* text = nullptr;
 	CountsCtx cnt; bool fold_records = false;
+	uint32_t jump_w = 1;
 	void* comm = nullptr; int comm_rank = 0, comm_size = 1; cudaStream_t comm_st = nullptr;      // NCCL communicator (cf_multi.cuh)
 };
 
@@ -1804,6 +1814,7 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 	else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
 	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
 	{ const char* rc0 = getenv("CFB_ROWS_CAP"); if(rc0) c->rows_cap0 = strtoull(rc0, NULL, 10); }
+	{ const char* jw = getenv("CFB_JUMP_W"); c->jump_w = jw ? (uint32_t)std::min(std::max(atoi(jw), 1), 8) : 1u; }
 	const char* cnt = getenv("CFB_COUNT");
 	c->count = cnt ? (cnt[0] == '1' ? 1 : (cnt[0] == '2' ? 2 : 0)) : 0;
 	#undef CKC
@@ -1896,9 +1907,11 @@ static int stage_batch(cfb_ctx* c, Slot& s, const cfb_batch* b) {
 	if(b->n_units >= (1ull << 30)) return fail(CFB_EINVAL, "batch too large (n_units must be < 2^30)");
 	const uint64_t n = b->n_units; const int nm = b->n_mates;
 	uint32_t maxlen = 0;
-	for(int m = 0; m < nm; m++) for(uint64_t i = 0; i < n; i++) {
-		if(b->off[m][i] + b->len[m][i] > b->n_bases) return fail(CFB_EINVAL, "unit %llu mate %d exceeds n_bases", (unsigned long long)i, m + 1);
-		maxlen = std::max(maxlen, b->len[m][i]);
+	for(int m = 0; m < nm; m++) {       // branch-free validation pass (vectorises); the offender is looked up only when there is one
+		const uint64_t* O = b->off[m]; const uint32_t* L = b->len[m]; const uint64_t nb = b->n_bases; uint32_t mx = 0; uint64_t bad = 0;
+		for(uint64_t i = 0; i < n; i++) { const uint32_t l = L[i]; mx = l > mx ? l : mx; bad |= (uint64_t)(O[i] + l > nb); }
+		if(bad) { for(uint64_t i = 0; i < n; i++) if(O[i] + L[i] > nb) return fail(CFB_EINVAL, "unit %llu mate %d exceeds n_bases", (unsigned long long)i, m + 1); }
+		maxlen = std::max(maxlen, mx);
 	}
 	if(maxlen > 60000) return fail(CFB_EINVAL, "read longer than 60000 bases");
 	CK(s.d_bases.ensure(b->n_bases + 16)); CK(s.d_off.ensure(n * nm)); CK(s.d_len.ensure(n * nm)); CK(s.d_flags.ensure(n));
@@ -1968,8 +1981,13 @@ static int stage_batch_packed(cfb_ctx* c, Slot& s, const cfb_batch_packed* b) {
 		return fail(CFB_EINVAL, "malformed cfb_batch_packed");
 	if(b->n_units >= (1ull << 30)) return fail(CFB_EINVAL, "batch too large (n_units must be < 2^30)");
 	const uint64_t n = b->n_units; const int nm = b->n_mates;
-	uint32_t maxlen = 0; uint64_t need_words = 0;
-	for(int m = 0; m < nm; m++) for(uint64_t i = 0; i < n; i++) { maxlen = std::max(maxlen, b->len[m][i]); need_words += ((uint64_t)b->len[m][i] + 31) >> 5; }
+	// one branch-free pass per mate over the lengths (it vectorises: this runs on the submitting thread, once per batch)
+	uint32_t maxlen = 0; uint64_t need_words = 0, mate_words[2] = {0, 0};
+	for(int m = 0; m < nm; m++) {
+		const uint32_t* L = b->len[m]; uint32_t mx = 0; uint64_t w = 0;
+		for(uint64_t i = 0; i < n; i++) { const uint32_t l = L[i]; mx = l > mx ? l : mx; w += (l + 31u) >> 5; }
+		maxlen = std::max(maxlen, mx); mate_words[m] = w; need_words += w;
+	}
 	if(need_words != b->n_words) return fail(CFB_EINVAL, "cfb_batch_packed: n_words is %llu, the lengths need %llu", (unsigned long long)b->n_words, (unsigned long long)need_words);
 	if(maxlen > 60000) return fail(CFB_EINVAL, "read longer than 60000 bases");
 	const uint64_t scan_blocks = (n + kScanBlock * kScanPer - 1) / (kScanBlock * kScanPer);
@@ -2007,7 +2025,7 @@ static int stage_batch_packed(cfb_ctx* c, Slot& s, const cfb_batch_packed* b) {
 		k_scan_apply<<<(unsigned)scan_blocks, kScanBlock, 0, s.st>>>(s.d_wlen.p, n, s.bsum.p, (const uint64_t*)(s.scal.p + 5), s.d_woff.p);
 		if(W) k_unpack<<<(unsigned)((n * W + 255) / 256), 256, 0, s.st>>>(s.d_words.p, s.d_woff.p, wbase, s.d_len.p + m * n, n, W, s.d_bases.p, s.d_off.p + m * n);
 		c->launches += 5;
-		for(uint64_t i = 0; i < n; i++) wbase += ((uint64_t)b->len[m][i] + 31) >> 5;      // mate 2 starts after all of mate 1 (host knows the lengths)
+		wbase += mate_words[m];      // mate 2 starts after all of mate 1
 	}
 	if(b->n_n) { k_set_n<<<(unsigned)((b->n_n + 255) / 256), 256, 0, s.st>>>(s.d_npos.p, b->n_n, s.d_bases.p, b->n_words * 32); c->launches++; }
 	CK(cudaGetLastError());
@@ -2046,7 +2064,7 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	if(stage == 0) {
 		SearchArgs sa; sa.v = c->view; sa.p = c->prm; sa.b = s.bv; sa.hits = s.hits.p; sa.nhits = s.nhits.p; sa.cap = s.cap;
 		const uint32_t W = (s.maxlen + 31) / 32 + 1;
-		sa.pk = s.pk.p; sa.nm = s.nm.p; sa.W = W;
+		sa.pk = s.pk.p; sa.nm = s.nm.p; sa.W = W; sa.jump_w = c->jump_w;
 		{ PackArgs pa; pa.b = s.bv; pa.pk = s.pk.p; pa.nm = s.nm.p; pa.W = W;
 		  k_pack<<<(unsigned)((ntasks * W + 127) / 128), 128, 0, s.st>>>(pa); c->launches++; }
 		sa.task_ctr = (unsigned int*)(s.scal.p + 0); sa.task_ctr64 = s.scal.p + 0; sa.ntasks = (uint32_t)ntasks; sa.overflow = (unsigned int*)(s.scal.p + 2); sa.ctr = ctr;
