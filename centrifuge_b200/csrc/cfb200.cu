@@ -912,7 +912,53 @@ struct UnitArgs {
 	Entry* entries; TaxCnt* tcs; OutRec* recs_sparse; uint32_t* nout;
 	unsigned int* overflow;
 	Counters* ctr;
+	const uint32_t* perm;       // processing order of the units (k_unit_scatter), null = natural order
 };
+
+// ---------------------------------------------------------------------------------------
+// Processing order of the per-unit kernels.  A thread's work in k_prep / k_score grows with the hits its unit carries
+// (ncu: 12 and 5 of 32 lanes active on average -- a few heavy units keep their warp while the others idle), so units are
+// binned by that number, heavy bins first: the lanes of a warp then run about the same trip counts.  Results are
+// written by unit index, so the order changes nothing but speed; within a bin the order is whatever the atomics give.
+// ---------------------------------------------------------------------------------------
+static const int kBins = 16;
+struct BinArgs { BatchView b; const uint32_t* nhits; unsigned int* hist; uint32_t* perm; };
+__device__ __forceinline__ uint32_t unit_key(const BinArgs& a, uint32_t unit) {
+	uint32_t tot = 0;
+	for(int m = 0; m < a.b.n_mates; m++) {
+		const size_t t0 = ((size_t)unit * a.b.n_mates + m) * 2;
+		const uint32_t r0 = a.nhits[t0], r1 = a.nhits[t0 + 1];
+		const bool drop = ((r0 | r1) & 0x80000000u) != 0;          // a strand without a long hit is read only if both have one (load_unit)
+		tot += (drop && (r0 & 0x80000000u)) ? 0u : (r0 & 0x7fffffffu);
+		tot += (drop && (r1 & 0x80000000u)) ? 0u : (r1 & 0x7fffffffu);
+	}
+	return tot < (uint32_t)kBins ? tot : (uint32_t)kBins - 1u;
+}
+__global__ void __launch_bounds__(256) k_unit_key(const BinArgs a) {
+	__shared__ unsigned int sh[kBins];
+	if(threadIdx.x < kBins) sh[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
+	if(unit < a.b.n_units) atomicAdd(&sh[unit_key(a, unit)], 1u);
+	__syncthreads();
+	if(threadIdx.x < kBins && sh[threadIdx.x]) atomicAdd(&a.hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_unit_scatter(const BinArgs a) {
+	__shared__ unsigned int base[kBins];
+	if(threadIdx.x == 0) { unsigned int run = 0; for(int k = kBins - 1; k >= 0; k--) { base[k] = run; run += a.hist[k]; } }     // heavy bins first
+	__syncthreads();
+	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = unit < a.b.n_units;
+	const uint32_t key = live ? unit_key(a, unit) : 0xffffffffu;
+	const uint32_t peers = __match_any_sync(0xffffffffu, key);
+	if(live) {
+		const uint32_t lane = threadIdx.x & 31, leader = (uint32_t)__ffs(peers) - 1u;
+		unsigned int start = 0;
+		if(lane == leader) start = atomicAdd(&a.hist[kBins + key], (unsigned int)__popc(peers));
+		start = __shfl_sync(peers, start, leader);
+		a.perm[base[key] + start + __popc(peers & ((1u << lane) - 1u))] = unit;
+	}
+}
 
 __device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, UnitHits& u, const uint8_t* fw[2]) {
 	const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
@@ -940,8 +986,9 @@ __device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, Unit
 // two steps on lists that are already final (after the row buffer had to grow).
 template <int MINB, bool EMIT_ONLY>
 __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
-	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool live = unit < a.b.n_units;
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = slot < a.b.n_units;
+	const uint32_t unit = live ? (a.perm ? a.perm[slot] : slot) : 0u;
 	UnitHits u; const uint8_t* fw[2];
 	uint64_t rows = 0; bool have = false;
 	if(live && (have = load_unit(a, unit, u, fw))) {
@@ -995,8 +1042,9 @@ __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
 static const int kLocalMap = 4;
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_score(const UnitArgs a) {
-	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
-	if(unit >= a.b.n_units) return;
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if(slot >= a.b.n_units) return;
+	const uint32_t unit = a.perm ? a.perm[slot] : slot;
 	uint32_t no = 0;
 	const uint64_t off = a.row_off[unit], n = a.nrows[unit];
 	if(n > 0 && *a.row_total <= a.rows_cap) {
@@ -1671,6 +1719,7 @@ struct Slot {
 	DBuf<unsigned long long> scal;    // [0] search task ctr (u32 used), [1] resolve ctr, [2] overflow, [3] total rows, [4] total recs
 	HBuf<unsigned long long> h_scal;
 	HBuf<OutRec> h_recs; HBuf<uint32_t> h_rec_off;
+	DBuf<uint32_t> perm; DBuf<unsigned int> binh;     // processing order of the per-unit kernels + its histogram / cursors
 	DBuf<unsigned long long> cnt;     // this batch's per-taxon counters (record path), added to the context's totals at wait time
 	bool folded = false, is_text = false, commit_pending = false;
 	// batch bookkeeping
@@ -1681,7 +1730,7 @@ struct Slot {
 		h_bases.release(); h_off.release(); h_len.release(); h_flags.release(); d_bases.release(); d_off.release(); d_len.release(); d_flags.release();
 		h_words.release(); d_words.release(); d_npos.release(); d_woff.release(); d_wlen.release();
 		pk.release(); nm.release(); hits.release(); nhits.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
-		sparse.release(); nout.release(); out_off.release(); dense.release(); rec_off32.release(); scal.release(); h_scal.release(); h_recs.release(); h_rec_off.release(); cnt.release();
+		sparse.release(); nout.release(); out_off.release(); dense.release(); rec_off32.release(); scal.release(); h_scal.release(); h_recs.release(); h_rec_off.release(); cnt.release(); perm.release(); binh.release();
 		for(int i = 0; i < 6; i++) if(ev[i]) cudaEventDestroy(ev[i]);
 		if(st) cudaStreamDestroy(st);
 	}
@@ -1717,7 +1766,7 @@ struct cfb_ctx {
 	uint64_t rows_cap0 = 0;       // CFB_ROWS_CAP: initial row-buffer capacity (tests force the grow-and-re-run path with it)
 	TextCtx* text = nullptr;
 	CountsCtx cnt; bool fold_records = false;
-	uint32_t jump_w = 1;
+	uint32_t jump_w = 1; bool bin_units = true;
 	void* comm = nullptr; int comm_rank = 0, comm_size = 1; cudaStream_t comm_st = nullptr;      // NCCL communicator (cf_multi.cuh)
 };
 
@@ -1814,6 +1863,7 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 	else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
 	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
 	{ const char* rc0 = getenv("CFB_ROWS_CAP"); if(rc0) c->rows_cap0 = strtoull(rc0, NULL, 10); }
+	{ const char* bu = getenv("CFB_BIN_UNITS"); c->bin_units = !(bu && bu[0] == '0'); }
 	{ const char* jw = getenv("CFB_JUMP_W"); c->jump_w = jw ? (uint32_t)std::min(std::max(atoi(jw), 1), 8) : 1u; }
 	const char* cnt = getenv("CFB_COUNT");
 	c->count = cnt ? (cnt[0] == '1' ? 1 : (cnt[0] == '2' ? 2 : 0)) : 0;
@@ -2061,6 +2111,8 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	ua.nrows = s.nrows.p; ua.row_off = s.row_off.p; ua.row_total = s.scal.p + 3; ua.rows = s.rows.p; ua.ids = s.ids.p; ua.rows_cap = s.rows_cap;
 	ua.entries = s.entries.p; ua.tcs = s.tcs.p; ua.recs_sparse = s.sparse.p; ua.nout = s.nout.p;
 	ua.overflow = (unsigned int*)(s.scal.p + 2); ua.ctr = ctr;
+	ua.perm = nullptr;
+	if(c->bin_units) { CK(s.perm.ensure(n)); CK(s.binh.ensure(2 * kBins)); ua.perm = s.perm.p; }
 	if(stage == 0) {
 		SearchArgs sa; sa.v = c->view; sa.p = c->prm; sa.b = s.bv; sa.hits = s.hits.p; sa.nhits = s.nhits.p; sa.cap = s.cap;
 		const uint32_t W = (s.maxlen + 31) / 32 + 1;
@@ -2086,6 +2138,13 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 		search_kernel(variant, c->count)<<<blocks, kSearchThreads, 0, s.st>>>(sa);
 		c->launches++;
 		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
+		if(ua.perm) {
+			BinArgs ba; ba.b = s.bv; ba.nhits = s.nhits.p; ba.hist = s.binh.p; ba.perm = s.perm.p;
+			CK(cudaMemsetAsync(s.binh.p, 0, 2 * kBins * sizeof(unsigned int), s.st));
+			k_unit_key<<<(unsigned)((n + 255) / 256), 256, 0, s.st>>>(ba);
+			k_unit_scatter<<<(unsigned)((n + 255) / 256), 256, 0, s.st>>>(ba);
+			c->launches += 2;
+		}
 		k_prep<8, false><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;          // <= 64 registers (measured best of 72 / 64 / 40)
 	} else {
 		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
