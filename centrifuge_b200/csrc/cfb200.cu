@@ -39,7 +39,7 @@ struct SearchArgs {
 	unsigned int* overflow;
 	Counters* ctr;
 	const uint64_t* pk; const uint32_t* nm; uint32_t W;   // packed reads (k_pack)
-	uint32_t jump_w;                                      // widest range advanced eight bases per gather through walk8 (CFB_JUMP_W)
+	uint32_t jump_w;                                      // widest range advanced eight bases per gather through walk8 (CFB_JUMP_W, default 4)
 };
 
 // row -> (side, offset in side).  Rows are < 2^39 for any index that fits in HBM, so row>>7 fits
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 	const uint32_t fdk = (uint32_t)a.v.ftabd_base;
 	ReadRegs<RW> rd;
 	uint64_t top = 0, bot = 0, fi = 0;
-	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0, slow_until = 0, fail_w = 0;
+	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0, slow_until = 0, fail_w = 0, fail_at = 0xffffffffu;
 	bool nolong = true;      // no hit of this strand reaches min_hitlen (kListNoLong tells the per-unit kernels)
 	int mode = M_NEED;
 	unsigned long long c_ps = 0, c_ft = 0, c_sides = 0, c_lf = 0;
@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 						const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
 						nh = 0; rlen = a.b.len[mate][unit];
 						if(!((fl >> mate) & 1) || rlen == 0) a.nhits[tid] = 0;          // filtered mate: stays M_NEED
-						else { rd.load(a.pk + (size_t)tid * a.W, a.nm + (size_t)tid * a.W, a.W); cur = 0; slow_until = 0; fail_w = 0; nolong = true; start_search(); }
+						else { rd.load(a.pk + (size_t)tid * a.W, a.nm + (size_t)tid * a.W, a.W); cur = 0; slow_until = 0; fail_w = 0; fail_at = 0xffffffffu; nolong = true; start_search(); }
 					} else mode = M_DONE;
 				}
 				if(__any_sync(0xffffffffu, want && !got)) more = false;      // global counter ran past the end
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 		// instead of one per iteration (ncu, profiles/r02: stalls at the K-mer-table consumer with 4 of 32 lanes active).
 		int c = 4;
 		const bool lf = mode == M_LF;
-		bool range = false, jump = false;
+		bool range = false, jump = false, known_fail = false;
 		const void* p0 = nullptr; const void* p1 = nullptr; uint32_t sub = 0;
 		if(mode == M_FTABD) {                                                // 2 bits of the death-depth table
 			const uint64_t idx = ((fi & ((1ull << (2 * fdk)) - 1ull)) << 6) | (fi >> (2 * fdk));
@@ -796,7 +796,8 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 			if(c <= 3) {
 				range = (bot - top) != 1;
 				const uint64_t width = bot - top;
-				if(w8 && width <= (uint64_t)a.jump_w && (dep >= slow_until || width < (uint64_t)fail_w) && rlen - dep >= 8 && bot <= a.v.walk8_rows) {
+				if(dep == fail_at && !range) known_fail = true;      // the walk8 entry already said that this step of the single row fails: no request
+				else if(w8 && width <= (uint64_t)a.jump_w && (dep >= slow_until || width < (uint64_t)fail_w) && rlen - dep >= 8 && bot <= a.v.walk8_rows) {
 					// Eight steps in one gather: while the walk holds a single row -- or a narrow range -- and the read's next eight
 					// bases are the ones stored for its first AND its last row.  LF keeps the order of rows that continue with the
 					// same base, so the range survives the eight steps intact exactly when both end rows do and their images are
@@ -852,9 +853,18 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 			   && (width == 1 || ((wl >> 40) == (w >> 40) && (wl & kWalkRowMask) - (w & kWalkRowMask) == width - 1))) {
 				top = w & kWalkRowMask; bot = top + width; dep += 8;
 				if(dep >= rlen) hit_and_restart();
-			} else { slow_until = dep + 8; fail_w = (uint32_t)width; }   // some row leaves within the next eight steps: take them one by one (a narrower range may try again)
+			} else {      // some row leaves within the next eight steps: take them one by one (a narrower range may try again)
+				slow_until = dep + 8; fail_w = (uint32_t)width;
+				if(width == 1) {      // a single row: the entry tells which step ends the hit (first stored base that differs, an N, or the '$' row)
+					const uint32_t diff = (uint32_t)(((w >> 40) ^ win) & 0xffffull), nb = nwin & 0xffu, nv = (uint32_t)(w >> 56) & 0xffu;
+					uint32_t good = diff ? (uint32_t)(__ffs(diff) - 1) >> 1 : 8u;
+					if(nb) good = min(good, (uint32_t)(__ffs(nb) - 1));
+					good = min(good, nv);
+					fail_at = good < 8u ? dep + good : 0xffffffffu;
+				}
+			}
 		} else if(lf) {
-			bool fail = c > 3;
+			bool fail = c > 3 || known_fail;
 			uint64_t t = 0, b = 0;
 			if(!fail) {
 				const uint32_t oT = (uint32_t)(top & 63), oB = (uint32_t)(bot & 63);
@@ -912,53 +922,7 @@ struct UnitArgs {
 	Entry* entries; TaxCnt* tcs; OutRec* recs_sparse; uint32_t* nout;
 	unsigned int* overflow;
 	Counters* ctr;
-	const uint32_t* perm;       // processing order of the units (k_unit_scatter), null = natural order
 };
-
-// ---------------------------------------------------------------------------------------
-// Processing order of the per-unit kernels.  A thread's work in k_prep / k_score grows with the hits its unit carries
-// (ncu: 12 and 5 of 32 lanes active on average -- a few heavy units keep their warp while the others idle), so units are
-// binned by that number, heavy bins first: the lanes of a warp then run about the same trip counts.  Results are
-// written by unit index, so the order changes nothing but speed; within a bin the order is whatever the atomics give.
-// ---------------------------------------------------------------------------------------
-static const int kBins = 16;
-struct BinArgs { BatchView b; const uint32_t* nhits; unsigned int* hist; uint32_t* perm; };
-__device__ __forceinline__ uint32_t unit_key(const BinArgs& a, uint32_t unit) {
-	uint32_t tot = 0;
-	for(int m = 0; m < a.b.n_mates; m++) {
-		const size_t t0 = ((size_t)unit * a.b.n_mates + m) * 2;
-		const uint32_t r0 = a.nhits[t0], r1 = a.nhits[t0 + 1];
-		const bool drop = ((r0 | r1) & 0x80000000u) != 0;          // a strand without a long hit is read only if both have one (load_unit)
-		tot += (drop && (r0 & 0x80000000u)) ? 0u : (r0 & 0x7fffffffu);
-		tot += (drop && (r1 & 0x80000000u)) ? 0u : (r1 & 0x7fffffffu);
-	}
-	return tot < (uint32_t)kBins ? tot : (uint32_t)kBins - 1u;
-}
-__global__ void __launch_bounds__(256) k_unit_key(const BinArgs a) {
-	__shared__ unsigned int sh[kBins];
-	if(threadIdx.x < kBins) sh[threadIdx.x] = 0;
-	__syncthreads();
-	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
-	if(unit < a.b.n_units) atomicAdd(&sh[unit_key(a, unit)], 1u);
-	__syncthreads();
-	if(threadIdx.x < kBins && sh[threadIdx.x]) atomicAdd(&a.hist[threadIdx.x], sh[threadIdx.x]);
-}
-__global__ void __launch_bounds__(256) k_unit_scatter(const BinArgs a) {
-	__shared__ unsigned int base[kBins];
-	if(threadIdx.x == 0) { unsigned int run = 0; for(int k = kBins - 1; k >= 0; k--) { base[k] = run; run += a.hist[k]; } }     // heavy bins first
-	__syncthreads();
-	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool live = unit < a.b.n_units;
-	const uint32_t key = live ? unit_key(a, unit) : 0xffffffffu;
-	const uint32_t peers = __match_any_sync(0xffffffffu, key);
-	if(live) {
-		const uint32_t lane = threadIdx.x & 31, leader = (uint32_t)__ffs(peers) - 1u;
-		unsigned int start = 0;
-		if(lane == leader) start = atomicAdd(&a.hist[kBins + key], (unsigned int)__popc(peers));
-		start = __shfl_sync(peers, start, leader);
-		a.perm[base[key] + start + __popc(peers & ((1u << lane) - 1u))] = unit;
-	}
-}
 
 __device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, UnitHits& u, const uint8_t* fw[2]) {
 	const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
@@ -986,9 +950,8 @@ __device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, Unit
 // two steps on lists that are already final (after the row buffer had to grow).
 template <int MINB, bool EMIT_ONLY>
 __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool live = slot < a.b.n_units;
-	const uint32_t unit = live ? (a.perm ? a.perm[slot] : slot) : 0u;
+	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = unit < a.b.n_units;
 	UnitHits u; const uint8_t* fw[2];
 	uint64_t rows = 0; bool have = false;
 	if(live && (have = load_unit(a, unit, u, fw))) {
@@ -1042,9 +1005,8 @@ __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
 static const int kLocalMap = 4;
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_score(const UnitArgs a) {
-	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	if(slot >= a.b.n_units) return;
-	const uint32_t unit = a.perm ? a.perm[slot] : slot;
+	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
+	if(unit >= a.b.n_units) return;
 	uint32_t no = 0;
 	const uint64_t off = a.row_off[unit], n = a.nrows[unit];
 	if(n > 0 && *a.row_total <= a.rows_cap) {
@@ -1719,7 +1681,6 @@ struct Slot {
 	DBuf<unsigned long long> scal;    // [0] search task ctr (u32 used), [1] resolve ctr, [2] overflow, [3] total rows, [4] total recs
 	HBuf<unsigned long long> h_scal;
 	HBuf<OutRec> h_recs; HBuf<uint32_t> h_rec_off;
-	DBuf<uint32_t> perm; DBuf<unsigned int> binh;     // processing order of the per-unit kernels + its histogram / cursors
 	DBuf<unsigned long long> cnt;     // this batch's per-taxon counters (record path), added to the context's totals at wait time
 	bool folded = false, is_text = false, commit_pending = false;
 	// batch bookkeeping
@@ -1730,7 +1691,7 @@ struct Slot {
 		h_bases.release(); h_off.release(); h_len.release(); h_flags.release(); d_bases.release(); d_off.release(); d_len.release(); d_flags.release();
 		h_words.release(); d_words.release(); d_npos.release(); d_woff.release(); d_wlen.release();
 		pk.release(); nm.release(); hits.release(); nhits.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
-		sparse.release(); nout.release(); out_off.release(); dense.release(); rec_off32.release(); scal.release(); h_scal.release(); h_recs.release(); h_rec_off.release(); cnt.release(); perm.release(); binh.release();
+		sparse.release(); nout.release(); out_off.release(); dense.release(); rec_off32.release(); scal.release(); h_scal.release(); h_recs.release(); h_rec_off.release(); cnt.release();
 		for(int i = 0; i < 6; i++) if(ev[i]) cudaEventDestroy(ev[i]);
 		if(st) cudaStreamDestroy(st);
 	}
@@ -1766,7 +1727,7 @@ struct cfb_ctx {
 	uint64_t rows_cap0 = 0;       // CFB_ROWS_CAP: initial row-buffer capacity (tests force the grow-and-re-run path with it)
 	TextCtx* text = nullptr;
 	CountsCtx cnt; bool fold_records = false;
-	uint32_t jump_w = 1; bool bin_units = true;
+	uint32_t jump_w = 4;
 	void* comm = nullptr; int comm_rank = 0, comm_size = 1; cudaStream_t comm_st = nullptr;      // NCCL communicator (cf_multi.cuh)
 };
 
@@ -1863,8 +1824,7 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 	else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
 	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
 	{ const char* rc0 = getenv("CFB_ROWS_CAP"); if(rc0) c->rows_cap0 = strtoull(rc0, NULL, 10); }
-	{ const char* bu = getenv("CFB_BIN_UNITS"); c->bin_units = !(bu && bu[0] == '0'); }
-	{ const char* jw = getenv("CFB_JUMP_W"); c->jump_w = jw ? (uint32_t)std::min(std::max(atoi(jw), 1), 8) : 1u; }
+	{ const char* jw = getenv("CFB_JUMP_W"); c->jump_w = jw ? (uint32_t)std::min(std::max(atoi(jw), 1), 8) : 4u; }      // measured on the bench workload: 1: 3.57, 2: 3.50, 3: 3.46, 4: 3.43 ms per 2 M reads (profiles/r02_ab.txt)
 	const char* cnt = getenv("CFB_COUNT");
 	c->count = cnt ? (cnt[0] == '1' ? 1 : (cnt[0] == '2' ? 2 : 0)) : 0;
 	#undef CKC
@@ -2111,8 +2071,6 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	ua.nrows = s.nrows.p; ua.row_off = s.row_off.p; ua.row_total = s.scal.p + 3; ua.rows = s.rows.p; ua.ids = s.ids.p; ua.rows_cap = s.rows_cap;
 	ua.entries = s.entries.p; ua.tcs = s.tcs.p; ua.recs_sparse = s.sparse.p; ua.nout = s.nout.p;
 	ua.overflow = (unsigned int*)(s.scal.p + 2); ua.ctr = ctr;
-	ua.perm = nullptr;
-	if(c->bin_units) { CK(s.perm.ensure(n)); CK(s.binh.ensure(2 * kBins)); ua.perm = s.perm.p; }
 	if(stage == 0) {
 		SearchArgs sa; sa.v = c->view; sa.p = c->prm; sa.b = s.bv; sa.hits = s.hits.p; sa.nhits = s.nhits.p; sa.cap = s.cap;
 		const uint32_t W = (s.maxlen + 31) / 32 + 1;
@@ -2138,13 +2096,6 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 		search_kernel(variant, c->count)<<<blocks, kSearchThreads, 0, s.st>>>(sa);
 		c->launches++;
 		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));
-		if(ua.perm) {
-			BinArgs ba; ba.b = s.bv; ba.nhits = s.nhits.p; ba.hist = s.binh.p; ba.perm = s.perm.p;
-			CK(cudaMemsetAsync(s.binh.p, 0, 2 * kBins * sizeof(unsigned int), s.st));
-			k_unit_key<<<(unsigned)((n + 255) / 256), 256, 0, s.st>>>(ba);
-			k_unit_scatter<<<(unsigned)((n + 255) / 256), 256, 0, s.st>>>(ba);
-			c->launches += 2;
-		}
 		k_prep<8, false><<<ublocks, 128, 0, s.st>>>(ua); c->launches++;          // <= 64 registers (measured best of 72 / 64 / 40)
 	} else {
 		if(time_it) CK(cudaEventRecord(s.ev[1], s.st));

@@ -93,8 +93,7 @@ LAYOUT_VARIANTS = {
     "no_ftabd": {"CFB_FTABD": "0"},
     "ftabd_over_ftabk12": {"CFB_FTABK": "12"},
     "half_walk8": {"CFB_WALK8_ROWS": "300000"},
-    "range_jump_w3": {"CFB_JUMP_W": "3"},
-    "units_in_natural_order": {"CFB_BIN_UNITS": "0"},
+    "range_jump_w1": {"CFB_JUMP_W": "1"},
     "range_jump_w8_half_walk8": {"CFB_JUMP_W": "8", "CFB_WALK8_ROWS": "300000"},
     "no_tables": {"CFB_WALK8": "0", "CFB_RESOLVE_TABLE": "0", "CFB_FTABK": "10", "CFB_FTABD": "0"},
     "ftabk11": {"CFB_FTABK": "11"},
