@@ -1918,9 +1918,10 @@ static int stage_batch(cfb_ctx* c, Slot& s, const cfb_batch* b) {
 	const uint64_t n = b->n_units; const int nm = b->n_mates;
 	uint32_t maxlen = 0;
 	for(int m = 0; m < nm; m++) {       // branch-free validation pass (vectorises); the offender is looked up only when there is one
-		const uint64_t* O = b->off[m]; const uint32_t* L = b->len[m]; const uint64_t nb = b->n_bases; uint32_t mx = 0; uint64_t bad = 0;
-		for(uint64_t i = 0; i < n; i++) { const uint32_t l = L[i]; mx = l > mx ? l : mx; bad |= (uint64_t)(O[i] + l > nb); }
-		if(bad) { for(uint64_t i = 0; i < n; i++) if(O[i] + L[i] > nb) return fail(CFB_EINVAL, "unit %llu mate %d exceeds n_bases", (unsigned long long)i, m + 1); }
+		const uint64_t* O = b->off[m]; const uint32_t* L = b->len[m]; const uint64_t nb = b->n_bases; uint32_t mx = 0; uint64_t far = 0;
+		for(uint64_t i = 0; i < n; i++) { const uint32_t l = L[i]; mx = l > mx ? l : mx; }
+		for(uint64_t i = 0; i < n; i++) { const uint64_t e = O[i] + (uint64_t)L[i]; far = e > far ? e : far; }
+		if(far > nb) { for(uint64_t i = 0; i < n; i++) if(O[i] + L[i] > nb) return fail(CFB_EINVAL, "unit %llu mate %d exceeds n_bases", (unsigned long long)i, m + 1); }
 		maxlen = std::max(maxlen, mx);
 	}
 	if(maxlen > 60000) return fail(CFB_EINVAL, "read longer than 60000 bases");
