@@ -682,7 +682,11 @@ def _main(result):
             tj = json.load(f)
         if tj.get("workload_key") == "%d_%d_%d_%s" % (a.lens[0], a.lens[1], int(a.paired), a.genera):
             traffic = tj["dram_bytes_per_unit"] * win
-            traffic_src = "ncu --set full capture of k_search_t on this workload (%s), per %d-unit launch; not measured in this run" % (tj.get("file", "profiles/"), win)
+            per_launch_s = search_s / len(windows)
+            traffic_src = {"what": "ncu --set full capture of k_search_t on this workload (%s), scaled to a %d-unit launch; NOT measured in this run" % (tj.get("file", "profiles/"), win),
+                           "dram_frac_of_hbm_peak": traffic / per_launch_s / 1e9 / peak,
+                           "dram_read_gsectors_s": tj["dram_bytes_read"] / 32.0 / tj["units_in_capture"] * win / per_launch_s / 1e9,
+                           "random_sector_ceiling_gsectors_s": 34.5, "ceiling_source": "tools/gather_bench.cu on this part, profiles/r02_gather_bench.txt (32 / 64 / 128-byte gathers all top out at ~1.1 TB/s)"}
     roof = {"bound": "hbm", "kernel": "k_search_t", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src, "kernel_ms_per_launch": 1000 * search_s / len(windows), "launches_per_step": len(windows),
             "bytes_definition": "the product's own algorithmic bytes: load requests counted by the kernel (CFB_COUNT=2 pass over one window of this batch) x one 32-byte DRAM sector each",
