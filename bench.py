@@ -475,7 +475,7 @@ def _main(result):
     # longest read -- hit lists (maxlen/4+8 records of 24 B per strand), packed strands, ~12 rows per unit of scoring scratch
     E2E_SLOTS = 8
     lc = 128 if rd.lmax <= 128 else (160 if rd.lmax <= 160 else (320 if rd.lmax <= 320 else ((rd.lmax + 1023) // 1024) * 1024))    # the text operator sizes by length class
-    per_unit = rd.mates * ((lc / 4 + 8) * 48 + (lc // 32 + 1) * 24 + 3.5 * lc + 64) + 1776 + 160
+    per_unit = rd.mates * ((lc // 22 + 2) * 48 + (lc / 4 + 8) * 48 / 32 + (lc // 32 + 1) * 24 + 3.5 * lc + 64) + 1776 + 160     # long hits only + 1/32 regenerated lists
     headroom_gb = max(24.0, ((E2E_SLOTS * a.sub + a.chunk) * per_unit * 1.3 + float(rd.lens.sum()) + 8.0 * n * rd.mates * 2 + (3 << 30)) / 2 ** 30)
     os.environ.setdefault("CFB_HBM_HEADROOM_GB", "%.1f" % headroom_gb)
     t0 = time.time()

@@ -1,21 +1,18 @@
-// cf_kernels.cuh -- sm_100a kernels of the classification path.
+// cf_kernels.cuh -- shared declarations of the sm_100a kernels of the classification path (cfb200.cu).
 //
-// Work decomposition (one batch of units = reads or pairs):
-//   k_search   FM-index backward search, the bandwidth-bound hot loop.  A *group* of 8 lanes owns
-//              one (unit, mate, strand) greedy walk; a 128-byte side is fetched as 8 x 16-byte
-//              coalesced vector loads (one full line per group), rank = lane-local popcount on the
-//              masked 2-bit planes + 3-step shuffle reduction.  A warp runs 4 walks (= both strands
-//              of two reads / both mates of a pair); every loop iteration has exactly one fetch point
-//              shared by all groups of the warp (ftab entry or side pair), so independent walks keep
-//              4-8 lines in flight per warp.  Groups pull task chunks from a global counter.
-//   k_prep     thread per unit: extend / twin-removal / trim, strand choice, libstdc++-exact sort,
-//              count SA rows to resolve.
-//   k_scan_*   exclusive scan of the per-unit row counts (u32 -> u64 offsets).
-//   k_rows     thread per unit: write the SA rows in consumption order.
-//   k_resolve  group of 8 lanes per SA row: walk-left (LF on BWT[row]) to a sampled / boundary / '$'
-//              row, same cooperative side fetch; sample value read through the same fetch point.
-//   k_score    thread per unit: hit map, score finalisation, host rule, taxonomy-tree reduction, emit.
-//   k_compact  dense output records.
+// Work decomposition (one batch of units = reads or pairs), DESIGN.md section 4:
+//   k_pack       reads (1 byte/base) -> 2-bit strands in search order + N masks
+//   k_search_t   FM-index backward search, the hot loop: ONE THREAD per (unit, mate, strand) greedy walk over the
+//                re-cut device index (rank16: one 16-byte gather per rank query; K-mer, death-depth and walk8 tables
+//                delete dependent gathers); one fetch point per loop iteration for all 32 walks of a warp
+//   k_search<G>  the warp-cooperative A/B variant (G lanes per walk on the file's 128-byte sides, shuffle popcount):
+//                same results, issue-bound, 7x slower (profiles/r02_ncu_k_search_coop8_500k.txt); uses the
+//                cooperative side primitives below
+//   k_prep       thread per unit: extend / twin-removal / trim, strand choice, libstdc++-exact sort, row allocation,
+//                rows with the scoring plan in their high bits
+//   k_lookup / k_resolve_c   SA row -> sequence id (table gather / 4-lane walk-left on rank16)
+//   k_score      thread per unit: hit map, score finalisation, host rule, taxonomy-tree reduction, emit
+//   k_scan_*, k_compact, k_fold_counts   offsets, dense records, per-taxon counters
 #ifndef CF_KERNELS_CUH_
 #define CF_KERNELS_CUH_
 

@@ -40,6 +40,7 @@ struct SearchArgs {
 	Counters* ctr;
 	const uint64_t* pk; const uint32_t* nm; uint32_t W;   // packed reads (k_pack)
 	uint32_t jump_w;                                      // widest range advanced eight bases per gather through walk8 (CFB_JUMP_W, default 4)
+	uint32_t keep_short;                                  // store every hit (min_hitlen < 22, generic kernels); else only hits of >= kLongLen bases
 };
 
 // row -> (side, offset in side).  Rows are < 2^39 for any index that fits in HBM, so row>>7 fits
@@ -267,7 +268,7 @@ struct SearchCtx {
 			return true;
 		}
 	}
-	__device__ __forceinline__ void finish_task(Walk2& w) { if(gl == 0) a.nhits[w.tid] = w.nh; }
+	__device__ __forceinline__ void finish_task(Walk2& w) { if(gl == 0) a.nhits[w.tid] = (w.nh & 0x7fffu) | ((w.nh < 0x7fffu ? w.nh : 0x7fffu) << 15); }   // every hit stored; word format of nh_pack (defined further down)
 
 	// Starts partial searches at w.cur until one needs the ftab (mode M_FTAB) or work runs out.
 	__device__ __forceinline__ void start_search(Walk2& w) {
@@ -558,7 +559,22 @@ __global__ void k_build_ftab2(IndexView v, uint64_t n, uint64_t* ftab2) {
 	if(fi >= n) return;
 	ftab2[fi * 2] = ftab_hi(v, v.ftab[fi]); ftab2[fi * 2 + 1] = ftab_lo(v, v.ftab[fi + 1]);
 }
-static const uint32_t kListNoLong = 0x80000000u;             // flag in nhits[]: the strand has no hit of min_hitlen bases
+// nhits[] word of a strand list: hits stored (15 bits) | hits found (15 bits, saturating) << 15 | kListNoLong.  With
+// min_hitlen >= 22 the search kernel stores only hits of at least kLongLen bases: shorter ones are never counted
+// (classifier.h:299), sort after every stored hit (compareBWTHits puts len >= 22 first) and touch nothing else -- unless
+// both strands of a mate are in play (extension / twin removal, classifier.h:790-870) or a list is long enough for
+// introsort (> 16 hits, where libstdc++'s tie permutation may depend on every element).  In those rare cases k_prep
+// regenerates the full lists with the scalar twin of the kernel (search_strand_scalar) into a side buffer and points the
+// list at it: word = kListRegen | slot.  Nine of ten hits of a typical read are short, so this removes most of the hit
+// traffic (random partial-sector writes) and shrinks the per-read device footprint from ~3.6 KB to ~2.3 KB.
+static const uint32_t kListNoLong = 0x80000000u;             // the strand has no hit of min_hitlen bases
+static const uint32_t kListRegen = 0x40000000u;              // the list lives in the regeneration buffer, slot = low 30 bits (written by k_prep)
+static const uint32_t kLongLen = 22;
+__host__ __device__ __forceinline__ uint32_t nh_pack(uint32_t stored, uint32_t found, bool nolong) {
+	return (stored & 0x7fffu) | ((found < 0x7fffu ? found : 0x7fffu) << 15) | (nolong ? kListNoLong : 0u);
+}
+__host__ __device__ __forceinline__ uint32_t nh_stored(uint32_t w) { return w & 0x7fffu; }
+__host__ __device__ __forceinline__ uint32_t nh_found(uint32_t w) { return (w >> 15) & 0x7fffu; }
 static const uint64_t kOccMask = 0x7fffffffffffffffull;
 static const uint64_t kWalkRowMask = (1ull << 40) - 1ull;   // walk8 entry: row in the low 40 bits
 static const int kJumpRows __attribute__((unused)) = 1;     // widest range advanced through walk8 (the kernel is specialised for 1).  Ranges of 2-4 adjacent rows can take the same
@@ -701,7 +717,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 	const uint32_t fdk = (uint32_t)a.v.ftabd_base;
 	ReadRegs<RW> rd;
 	uint64_t top = 0, bot = 0, fi = 0;
-	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0, slow_until = 0, fail_w = 0, fail_at = 0xffffffffu;
+	uint32_t rlen = 0, tid = 0, cur = 0, dep = 0, offset = 0, nh = 0, nt = 0, slow_until = 0, fail_w = 0, fail_at = 0xffffffffu;
 	bool nolong = true;      // no hit of this strand reaches min_hitlen (kListNoLong tells the per-unit kernels)
 	int mode = M_NEED;
 	unsigned long long c_ps = 0, c_ft = 0, c_sides = 0, c_lf = 0;
@@ -710,16 +726,19 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 	bool more = true;      // warp-uniform: the global task counter is not exhausted yet
 
 	auto emit = [&](uint64_t t, uint64_t b, uint32_t off, uint32_t len) {
-		if(nh < a.cap) { HitRec* h = a.hits + (size_t)tid * a.cap + nh; h->top = t; h->bot = b; h->bwoff = off; h->len = len; }
-		else atomicExch(a.overflow, 1u);
-		nh++;
+		if(a.keep_short || len >= kLongLen) {
+			if(nh < a.cap) { HitRec* h = a.hits + (size_t)tid * a.cap + nh; h->top = t; h->bot = b; h->bwoff = off; h->len = len; }
+			else atomicExch(a.overflow, 1u);
+			nh++;
+		}
+		nt++;
 		if(len >= a.p.min_hitlen) nolong = false;
 	};
 	// searchForwardAndReverse restart policy (classifier.h:686-766): true = another partial search starts at cur
 	auto after_hit = [&](uint32_t hlen) -> bool {
 		bool done = cur >= rlen;
 		if(!done) { if(hlen > a.p.increment) cur += 1; if(cur + a.p.min_hitlen >= rlen) done = true; }
-		if(done) { a.nhits[tid] = nh | (nolong ? kListNoLong : 0u); mode = M_NEED; return false; }
+		if(done) { a.nhits[tid] = nh_pack(nh, nt, nolong); mode = M_NEED; return false; }
 		return true;
 	};
 	// partialSearch prologue (hi_aligner.h:939-982) at `cur`: ends in M_FTAB (fi set) or M_NEED
@@ -727,7 +746,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 		for(;;) {
 			if(COUNT == 1) c_ps++;
 			offset = cur;
-			if(rlen - cur < fc) { emit(kOff, kOff, offset, rlen - offset); a.nhits[tid] = nh | (nolong ? kListNoLong : 0u); mode = M_NEED; return; }
+			if(rlen - cur < fc) { emit(kOff, kOff, offset, rlen - offset); a.nhits[tid] = nh_pack(nh, nt, nolong); mode = M_NEED; return; }
 			uint64_t win; uint32_t nwin; rd.window(cur, win, nwin);
 			const uint32_t nbits = nwin & ((1u << fc) - 1u);
 			if(nbits) {
@@ -764,7 +783,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_t(const SearchArgs a)
 						const uint32_t unit = tid / per, rem = tid - unit * per;
 						const int mate = (int)(rem >> 1);
 						const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
-						nh = 0; rlen = a.b.len[mate][unit];
+						nh = 0; nt = 0; rlen = a.b.len[mate][unit];
 						if(!((fl >> mate) & 1) || rlen == 0) a.nhits[tid] = 0;          // filtered mate: stays M_NEED
 						else { rd.load(a.pk + (size_t)tid * a.W, a.nm + (size_t)tid * a.W, a.W); cur = 0; slow_until = 0; fail_w = 0; fail_at = 0xffffffffu; nolong = true; start_search(); }
 					} else mode = M_DONE;
@@ -922,9 +941,12 @@ struct UnitArgs {
 	Entry* entries; TaxCnt* tcs; OutRec* recs_sparse; uint32_t* nout;
 	unsigned int* overflow;
 	Counters* ctr;
+	HitRec* regen; uint32_t* regen_n; unsigned long long* regen_ctr; uint64_t regen_slots; uint32_t full_cap; uint32_t keep_short;
 };
 
-__device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, UnitHits& u, const uint8_t* fw[2]) {
+// found[r][st] receives the number of hits the search found for the list (0 for a regenerated list); tpos[r] the index of
+// the mate's first nhits word
+__device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, UnitHits& u, const uint8_t* fw[2], uint32_t found[2][2], size_t tpos[2]) {
 	const uint8_t fl = a.b.flags ? a.b.flags[unit] : 3;
 	u.n_mates = 0;
 	for(int m = 0; m < a.b.n_mates; m++) {
@@ -933,14 +955,20 @@ __device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, Unit
 		if(len == 0) continue;
 		const int r = u.n_mates++;
 		const size_t t0 = ((size_t)unit * a.b.n_mates + m) * 2;
-		const uint32_t raw0 = a.nhits[t0], raw1 = a.nhits[t0 + 1];
-		u.L[r][0] = a.hits + t0 * a.cap;       u.n[r][0] = min(raw0 & ~kListNoLong, a.cap);
-		u.L[r][1] = a.hits + (t0 + 1) * a.cap; u.n[r][1] = min(raw1 & ~kListNoLong, a.cap);
+		u.rdlen[r] = len; fw[r] = a.b.bases + a.b.off[m][unit]; tpos[r] = t0;
+		const uint32_t raw[2] = {a.nhits[t0], a.nhits[t0 + 1]};
+		for(int st = 0; st < 2; st++) {
+			if(raw[st] & kListRegen) {                            // regenerated by an earlier k_prep pass over this batch
+				const uint32_t slot = raw[st] & 0x3fffffffu;
+				u.L[r][st] = a.regen + (size_t)slot * a.full_cap; u.n[r][st] = a.regen_n[slot]; found[r][st] = 0;
+			} else {
+				u.L[r][st] = a.hits + (t0 + st) * a.cap; u.n[r][st] = min(nh_stored(raw[st]), a.cap); found[r][st] = nh_found(raw[st]);
+			}
+		}
 		// A strand list without a hit of min_hitlen bases matters only to the extension step, which needs such a hit on
 		// BOTH strands (classifier.h:790-802); everything later (trimming within a list, strand choice, counting,
 		// scoring) ignores or only shortens short hits.  So unless both strands have one, such a list is never read.
-		if((raw0 | raw1) & kListNoLong) { if(raw0 & kListNoLong) u.n[r][0] = 0; if(raw1 & kListNoLong) u.n[r][1] = 0; }
-		u.rdlen[r] = len; fw[r] = a.b.bases + a.b.off[m][unit];
+		if(!((raw[0] | raw[1]) & kListRegen) && ((raw[0] | raw[1]) & kListNoLong)) { if(raw[0] & kListNoLong) u.n[r][0] = 0; if(raw[1] & kListNoLong) u.n[r][1] = 0; }
 	}
 	return u.n_mates > 0;
 }
@@ -952,13 +980,28 @@ template <int MINB, bool EMIT_ONLY>
 __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
 	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool live = unit < a.b.n_units;
-	UnitHits u; const uint8_t* fw[2];
+	UnitHits u; const uint8_t* fw[2]; uint32_t found[2][2]; size_t tpos[2];
 	uint64_t rows = 0; bool have = false;
-	if(live && (have = load_unit(a, unit, u, fw))) {
+	if(live && (have = load_unit(a, unit, u, fw, found, tpos))) {
 		if(EMIT_ONLY) { CountRows cr(a.p, u); for_each_visit(a.p, u, cr); rows = cr.rows; }
 		else {
 			Counters local; Counters* lc = nullptr;
 			if(a.ctr) { memset(&local, 0, sizeof local); lc = &local; }
+			// Only the long hits were stored (see kListRegen): where the short ones can matter, run the strand's search again
+			// with the scalar twin of the kernel into the side buffer, and let the list point there from now on.
+			if(!a.keep_short) for(int r = 0; r < u.n_mates; r++) {
+				const bool both = u.n[r][0] > 0 && u.n[r][1] > 0;
+				for(int st = 0; st < 2; st++) {
+					if(u.n[r][st] == 0 || !(both || found[r][st] > 16)) continue;
+					const unsigned long long slot = atomicAdd(a.regen_ctr, 1ull);
+					if(slot >= a.regen_slots) { atomicExch(a.overflow, 4u); continue; }      // the host grows the side buffer and re-runs the batch
+					HitRec* L = a.regen + (size_t)slot * a.full_cap;
+					const uint32_t n = search_strand_scalar(a.v, a.p, fw[r], u.rdlen[r], st, L, a.full_cap, nullptr);
+					if(n > a.full_cap) atomicExch(a.overflow, 1u);
+					u.L[r][st] = L; u.n[r][st] = min(n, a.full_cap);
+					a.regen_n[slot] = u.n[r][st]; a.nhits[tpos[r] + st] = kListRegen | (uint32_t)slot;
+				}
+			}
 			// Hits the death-depth table ended carry no SA range.  A short hit's range can matter only through the twin
 			// removal (both strands in play, classifier.h:850-870) or through libstdc++'s tie permutation in lists long
 			// enough for introsort (> 16 hits): recompute the ranges there, exactly as partialSearch would.
@@ -1675,7 +1718,7 @@ struct Slot {
 	HBuf<uint64_t> h_words; DBuf<uint64_t> d_words, d_npos, d_woff; DBuf<uint32_t> d_wlen;      // packed input (cfb_batch_packed)
 	// work
 	DBuf<uint64_t> pk; DBuf<uint32_t> nm;
-	DBuf<HitRec> hits; DBuf<uint32_t> nhits; DBuf<uint32_t> nrows; DBuf<uint64_t> row_off; DBuf<uint64_t> bsum;
+	DBuf<HitRec> hits; DBuf<uint32_t> nhits; DBuf<HitRec> regen; DBuf<uint32_t> regen_n; uint64_t regen_slots = 0; uint32_t full_cap = 0; DBuf<uint32_t> nrows; DBuf<uint64_t> row_off; DBuf<uint64_t> bsum;
 	DBuf<uint64_t> rows; DBuf<uint32_t> ids; DBuf<Entry> entries; DBuf<TaxCnt> tcs; DBuf<OutRec> sparse;
 	DBuf<uint32_t> nout; DBuf<uint64_t> out_off; DBuf<OutRec> dense; DBuf<uint32_t> rec_off32;
 	DBuf<unsigned long long> scal;    // [0] search task ctr (u32 used), [1] resolve ctr, [2] overflow, [3] total rows, [4] total recs
@@ -1690,7 +1733,7 @@ struct Slot {
 	void release() {
 		h_bases.release(); h_off.release(); h_len.release(); h_flags.release(); d_bases.release(); d_off.release(); d_len.release(); d_flags.release();
 		h_words.release(); d_words.release(); d_npos.release(); d_woff.release(); d_wlen.release();
-		pk.release(); nm.release(); hits.release(); nhits.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
+		pk.release(); nm.release(); hits.release(); nhits.release(); regen.release(); regen_n.release(); nrows.release(); row_off.release(); bsum.release(); rows.release(); ids.release(); entries.release(); tcs.release();
 		sparse.release(); nout.release(); out_off.release(); dense.release(); rec_off32.release(); scal.release(); h_scal.release(); h_recs.release(); h_rec_off.release(); cnt.release();
 		for(int i = 0; i < 6; i++) if(ev[i]) cudaEventDestroy(ev[i]);
 		if(st) cudaStreamDestroy(st);
@@ -1727,7 +1770,8 @@ struct cfb_ctx {
 	uint64_t rows_cap0 = 0;       // CFB_ROWS_CAP: initial row-buffer capacity (tests force the grow-and-re-run path with it)
 	TextCtx* text = nullptr;
 	CountsCtx cnt; bool fold_records = false;
-	uint32_t jump_w = 4;
+	uint32_t jump_w = 4; bool keep_short = false;      // CFB_KEEP_SHORT=1: store every hit (A/B and tests)
+	uint64_t regen_slots0 = 0;    // CFB_REGEN_SLOTS: initial capacity of the list-regeneration buffer (tests force the grow-and-re-run path with it)
 	void* comm = nullptr; int comm_rank = 0, comm_size = 1; cudaStream_t comm_st = nullptr;      // NCCL communicator (cf_multi.cuh)
 };
 
@@ -1824,6 +1868,8 @@ extern "C" int cfb_ctx_create(const cfb_index* ix, const cfb_params* p, cfb_ctx*
 	else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve<false>, kSearchThreads, 0));
 	c->resolve_blocks = ix->sm_count * std::max(occ, 1);
 	{ const char* rc0 = getenv("CFB_ROWS_CAP"); if(rc0) c->rows_cap0 = strtoull(rc0, NULL, 10); }
+	{ const char* ks = getenv("CFB_KEEP_SHORT"); c->keep_short = ks && ks[0] == '1'; }
+	{ const char* rs = getenv("CFB_REGEN_SLOTS"); if(rs) c->regen_slots0 = strtoull(rs, NULL, 10); }
 	{ const char* jw = getenv("CFB_JUMP_W"); c->jump_w = jw ? (uint32_t)std::min(std::max(atoi(jw), 1), 8) : 4u; }      // measured on the bench workload: 1: 3.57, 2: 3.50, 3: 3.46, 4: 3.43 ms per 2 M reads (profiles/r02_ab.txt)
 	const char* cnt = getenv("CFB_COUNT");
 	c->count = cnt ? (cnt[0] == '1' ? 1 : (cnt[0] == '2' ? 2 : 0)) : 0;
@@ -2054,9 +2100,23 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	const uint32_t ublocks = (uint32_t)((n + 127) / 128);
 	const uint64_t scan_blocks = (n + kScanBlock * kScanPer - 1) / (kScanBlock * kScanPer);
 	if(n == 0) return CFB_OK;
+	// which search kernel runs decides what it stores: the thread-per-walk kernels keep only hits of >= kLongLen bases when
+	// min_hitlen allows it (see kListRegen), the generic / A-B kernels and small min_hitlen keep every hit
+	int variant = c->group;
+	if(variant == 1) { if(s.maxlen > 320) variant = 16; else if(s.maxlen > 160) variant = 100; else if(s.maxlen > 128) variant = 101; }   // longer reads: wider register window / windowed kernel
+	const bool pooled = variant == 1 || variant == 100 || variant == 101;
+	const bool keep_short = !pooled || c->prm.min_hitlen < kLongLen || c->keep_short;
 	if(stage == 0) {
-		if(s.cap == 0) s.cap = s.maxlen / 4 + 8;      // >= #Ns allowed by the N filter (0.15 len) + len/10 + slack
+		if(s.cap == 0) {
+			s.full_cap = s.maxlen / 4 + 8;      // >= #Ns allowed by the N filter (0.15 len) + len/10 + slack
+			s.cap = keep_short ? s.full_cap : s.maxlen / kLongLen + 2;       // hits of >= 22 bases do not overlap
+		}
 		CK(s.hits.ensure(ntasks * s.cap)); CK(s.nhits.ensure(ntasks));
+		if(!keep_short) {
+			s.regen_slots = std::max<uint64_t>(s.regen_slots, c->regen_slots0 ? c->regen_slots0 : std::max<uint64_t>(ntasks / 32, 1024));
+			CK(s.regen.ensure(s.regen_slots * s.full_cap)); CK(s.regen_n.ensure(s.regen_slots));
+			CK(cudaMemsetAsync(s.scal.p + 6, 0, sizeof(unsigned long long), s.st));
+		}
 		const uint32_t W = (s.maxlen + 31) / 32 + 1;
 		CK(s.pk.ensure(ntasks * W + 2)); CK(s.nm.ensure(ntasks * W + 2)); CK(s.nrows.ensure(n)); CK(s.row_off.ensure(n + 1));
 		CK(s.bsum.ensure(scan_blocks + 1)); CK(s.nout.ensure(n)); CK(s.out_off.ensure(n + 1)); CK(s.rec_off32.ensure(n + 1));
@@ -2072,16 +2132,14 @@ static int enqueue_kernels(cfb_ctx* c, Slot& s, int stage, bool time_it) {
 	ua.nrows = s.nrows.p; ua.row_off = s.row_off.p; ua.row_total = s.scal.p + 3; ua.rows = s.rows.p; ua.ids = s.ids.p; ua.rows_cap = s.rows_cap;
 	ua.entries = s.entries.p; ua.tcs = s.tcs.p; ua.recs_sparse = s.sparse.p; ua.nout = s.nout.p;
 	ua.overflow = (unsigned int*)(s.scal.p + 2); ua.ctr = ctr;
+	ua.regen = s.regen.p; ua.regen_n = s.regen_n.p; ua.regen_ctr = s.scal.p + 6; ua.regen_slots = s.regen_slots; ua.full_cap = s.full_cap; ua.keep_short = keep_short ? 1u : 0u;
 	if(stage == 0) {
 		SearchArgs sa; sa.v = c->view; sa.p = c->prm; sa.b = s.bv; sa.hits = s.hits.p; sa.nhits = s.nhits.p; sa.cap = s.cap;
 		const uint32_t W = (s.maxlen + 31) / 32 + 1;
-		sa.pk = s.pk.p; sa.nm = s.nm.p; sa.W = W; sa.jump_w = c->jump_w;
+		sa.pk = s.pk.p; sa.nm = s.nm.p; sa.W = W; sa.jump_w = c->jump_w; sa.keep_short = keep_short ? 1u : 0u;
 		{ PackArgs pa; pa.b = s.bv; pa.pk = s.pk.p; pa.nm = s.nm.p; pa.W = W;
 		  k_pack<<<(unsigned)((ntasks * W + 127) / 128), 128, 0, s.st>>>(pa); c->launches++; }
 		sa.task_ctr = (unsigned int*)(s.scal.p + 0); sa.task_ctr64 = s.scal.p + 0; sa.ntasks = (uint32_t)ntasks; sa.overflow = (unsigned int*)(s.scal.p + 2); sa.ctr = ctr;
-		int variant = c->group;
-		if(variant == 1) { if(s.maxlen > 320) variant = 16; else if(s.maxlen > 160) variant = 100; else if(s.maxlen > 128) variant = 101; }   // longer reads: wider register window / windowed kernel
-		const bool pooled = variant == 1 || variant == 100 || variant == 101;
 		const int lanes = (variant == 16 || pooled) ? 1 : variant;
 		int occ = 1;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, search_kernel(variant, c->count), kSearchThreads, 0));
@@ -2149,8 +2207,13 @@ static int finish_batch(cfb_ctx* c, Slot& s, bool time_it, bool to_host, cfb_res
 		CK(cudaStreamSynchronize(s.st));
 		const unsigned ovf = (unsigned)(s.h_scal.p[2] & 0xffffffffu);
 		const uint64_t total_rows = s.h_scal.p[3];
+		if(ovf == 4) {            // more lists needed regeneration than the side buffer holds: h_scal[6] tells how many
+			s.regen_slots = s.h_scal.p[6] + s.h_scal.p[6] / 4 + 1024; s.reran = true;
+			int rc = enqueue_kernels(c, s, 0, time_it); if(rc) return rc;
+			continue;
+		}
 		if(ovf == 1) {            // hit-list capacity: only possible when the caller's flags bypass the N filter
-			s.cap = s.maxlen + 2; s.reran = true;
+			s.cap = s.maxlen + 2; s.full_cap = s.maxlen + 2; s.reran = true;
 			int rc = enqueue_kernels(c, s, 0, time_it); if(rc) return rc;
 			continue;
 		}
