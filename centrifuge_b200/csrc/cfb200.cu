@@ -1045,7 +1045,7 @@ __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
 	if(rows && off + rows <= a.rows_cap) { EmitRows er(a.p, u, a.rows + off); for_each_visit(a.p, u, er); }   // else: the host grows the buffer and re-runs EMIT_ONLY
 }
 
-static const int kLocalMap = 4;
+static const int kLocalMap = 4;          // 16 measured slower (0.82 vs 0.63 ms per 2 M reads, profiles/r02_ab.txt): the bigger local frame costs more than the global scratch of the few heavy units
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_score(const UnitArgs a) {
 	const uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x;
