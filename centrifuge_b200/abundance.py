@@ -1,4 +1,6 @@
-"""Dense per-taxon read counters for the multi-GPU reduction.
+"""Host restatement of the per-taxon read counters -- what k_fold_counts / k_fmt_plan accumulate on the device and
+cfb_counts_allreduce sums over the GPUs.  Kept as the checker of those kernels (tests/test_gpu_multi.py) and for the gloo
+CPU test of the sharding logic (tests/test_multi_rank.py); the product path does not use it.
 
 `taxon_counts` restates what AlnSinkWrap::finishRead -> SpeciesMetrics::addSpeciesCounts (aln_sink.h:142-156,
 1861-1927) accumulate per read -- numReads for every reported assignment, numUniqueReads when exactly one
@@ -30,7 +32,6 @@ def taxon_counts(node_taxids, rec_off, recs, k=5):
     np.maximum.at(best, unit, score)
     top = score == best[unit]
     # rank of each top record inside its unit (hit-map order) to apply the k cap
-    idx_in_unit = np.arange(len(recs)) - np.repeat(rec_off[:-1].astype(np.int64), cnt)
     order = np.zeros(len(recs), dtype=np.int64)
     tops = np.nonzero(top)[0]
     tunit = unit[tops]
@@ -46,5 +47,4 @@ def taxon_counts(node_taxids, rec_off, recs, k=5):
     np.add.at(out[:, 0], pos, 1)
     uniq = nrep[unit[rep]] == 1
     np.add.at(out[:, 1], pos[uniq], 1)
-    _ = idx_in_unit
     return out
