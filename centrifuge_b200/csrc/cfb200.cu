@@ -564,8 +564,8 @@ __global__ void k_build_ftab2(IndexView v, uint64_t n, uint64_t* ftab2) {
 // (classifier.h:299), sort after every stored hit (compareBWTHits puts len >= 22 first) and touch nothing else -- unless
 // both strands of a mate are in play (extension / twin removal, classifier.h:790-870) or a list is long enough for
 // introsort (> 16 hits, where libstdc++'s tie permutation may depend on every element).  In those rare cases k_prep
-// regenerates the full lists with the scalar twin of the kernel (search_strand_scalar) into a side buffer and points the
-// list at it: word = kListRegen | slot.  Nine of ten hits of a typical read are short, so this removes most of the hit
+// regenerates the full lists with a one-thread version of the kernel's walk (search_strand_dev) into a side buffer and points
+// the list at it: word = kListRegen | slot.  Nine of ten hits of a typical read are short, so this removes most of the hit
 // traffic (random partial-sector writes) and shrinks the per-read device footprint from ~3.6 KB to ~2.3 KB.
 static const uint32_t kListNoLong = 0x80000000u;             // the strand has no hit of min_hitlen bases
 static const uint32_t kListRegen = 0x40000000u;              // the list lives in the regeneration buffer, slot = low 30 bits (written by k_prep)
@@ -944,6 +944,69 @@ struct UnitArgs {
 	HitRec* regen; uint32_t* regen_n; unsigned long long* regen_ctr; uint64_t regen_slots; uint32_t full_cap; uint32_t keep_short;
 };
 
+// One strand's whole greedy search by a single thread, with the device tables: the hits search_strand_scalar (cf_logic.h, the
+// twin the CPU tests pin against the oracle) would produce, but reached the way k_search_t reaches them -- K-mer jump, one
+// rank16 entry per step when top and bot share a block, eight bases per walk8 gather on a single row -- so that regenerating
+// a list costs ~30 dependent gathers instead of ~250.  Used by k_prep only (lists whose short hits matter).
+__device__ uint32_t search_strand_dev(const IndexView& v, const Params& p, const uint8_t* fw, uint32_t len, int strand, HitRec* hits, uint32_t cap) {
+	const ulonglong2* r16 = reinterpret_cast<const ulonglong2*>(v.rank16);
+	const ulonglong2* ftab2 = reinterpret_cast<const ulonglong2*>(v.ftab2);
+	const ulonglong2* ftabk = reinterpret_cast<const ulonglong2*>(v.ftabk);
+	const uint32_t fc = (uint32_t)v.ftab_chars, fk = v.ftabk ? (uint32_t)v.ftabk_chars : 0u;
+	auto base = [&](uint32_t d) -> int { return seq_at(fw, len, strand, len - 1 - d); };     // the base consumed at search depth d
+	uint32_t cur = 0, n = 0;
+	if(len == 0) return 0;
+	for(;;) {
+		HitRec h; h.bwoff = cur; uint32_t new_cur; bool done = false;
+		const uint32_t offset = cur;
+		if(len - cur < fc) { h.top = h.bot = kOff; h.len = len - offset; new_cur = len; done = true; }
+		else {
+			uint32_t firstn = 0xffffffffu; uint64_t fi = 0;
+			const uint32_t span = (fk && len - cur >= fk) ? fk : fc;
+			for(uint32_t i = 0; i < span; i++) { const int c = base(cur + i); if(c > 3) { firstn = i; break; } fi |= (uint64_t)c << (2 * i); }
+			if(firstn < fc) { new_cur = cur + firstn + 1; h.top = h.bot = kOff; h.len = new_cur - offset; done = new_cur >= len; }
+			else {
+				uint64_t top = 0, bot = 0; uint32_t dep = 0; bool have = false;
+				if(span == fk && fk > fc && firstn == 0xffffffffu) { const ulonglong2 e = __ldg(ftabk + fi); if(e.y > e.x) { top = e.x; bot = e.y; dep = cur + fk; have = true; } }
+				if(!have) { const ulonglong2 e = __ldg(ftab2 + (fi & ((1ull << (2 * fc)) - 1ull))); top = e.x; bot = e.y; dep = cur + fc; }
+				if(bot <= top) { h.top = h.bot = kOff; h.len = dep - offset; new_cur = dep; done = dep >= len; }
+				else {
+					while(dep < len) {
+						const int c = base(dep);
+						if(c > 3) break;
+						if(bot - top == 1) {
+							if(v.walk8 && top < v.walk8_rows && len - dep >= 8) {        // eight bases in one gather
+								const uint64_t e = __ldg(v.walk8 + top);
+								bool ok = (e >> 56) == 8;
+								for(uint32_t j = 0; ok && j < 8; j++) ok = base(dep + j) == (int)((e >> (40 + 2 * j)) & 3);
+								if(ok) { top = e & kWalkRowMask; bot = top + 1; dep += 8; continue; }
+							}
+							const ulonglong2 e = __ldg(r16 + (top >> 6) * 4 + c);
+							if(!((e.y >> (top & 63)) & 1ull)) break;                      // mapLF1: BWT[top] must be c ('$' has no bit)
+							top = v.fchr[c] + (e.x & kOccMask) + (uint64_t)__popcll(e.y & ((1ull << (top & 63)) - 1ull)); bot = top + 1; dep++;
+						} else {
+							const ulonglong2 et = __ldg(r16 + (top >> 6) * 4 + c);
+							const ulonglong2 eb = (bot >> 6) == (top >> 6) ? et : __ldg(r16 + (bot >> 6) * 4 + c);
+							const uint64_t t = v.fchr[c] + (et.x & kOccMask) + (uint64_t)__popcll(et.y & ((1ull << (top & 63)) - 1ull));
+							const uint64_t b = v.fchr[c] + (eb.x & kOccMask) + (uint64_t)__popcll(eb.y & ((1ull << (bot & 63)) - 1ull));
+							if(b <= t) break;
+							top = t; bot = b; dep++;
+						}
+					}
+					h.top = top; h.bot = bot; h.len = dep - offset; new_cur = dep; done = dep >= len;
+				}
+			}
+		}
+		if(n < cap) hits[n] = h;
+		n++;
+		cur = new_cur;
+		if(done) break;
+		if(h.len > p.increment) cur += 1;
+		if(cur + p.min_hitlen >= len) break;
+	}
+	return n;
+}
+
 // found[r][st] receives the number of hits the search found for the list (0 for a regenerated list); tpos[r] the index of
 // the mate's first nhits word
 __device__ __forceinline__ bool load_unit(const UnitArgs& a, uint32_t unit, UnitHits& u, const uint8_t* fw[2], uint32_t found[2][2], size_t tpos[2]) {
@@ -988,7 +1051,7 @@ __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
 			Counters local; Counters* lc = nullptr;
 			if(a.ctr) { memset(&local, 0, sizeof local); lc = &local; }
 			// Only the long hits were stored (see kListRegen): where the short ones can matter, run the strand's search again
-			// with the scalar twin of the kernel into the side buffer, and let the list point there from now on.
+			// on this thread (search_strand_dev) into the side buffer, and let the list point there from now on.
 			if(!a.keep_short) for(int r = 0; r < u.n_mates; r++) {
 				const bool both = u.n[r][0] > 0 && u.n[r][1] > 0;
 				for(int st = 0; st < 2; st++) {
@@ -996,7 +1059,7 @@ __global__ void __launch_bounds__(128, MINB) k_prep(const UnitArgs a) {
 					const unsigned long long slot = atomicAdd(a.regen_ctr, 1ull);
 					if(slot >= a.regen_slots) { atomicExch(a.overflow, 4u); continue; }      // the host grows the side buffer and re-runs the batch
 					HitRec* L = a.regen + (size_t)slot * a.full_cap;
-					const uint32_t n = search_strand_scalar(a.v, a.p, fw[r], u.rdlen[r], st, L, a.full_cap, nullptr);
+					const uint32_t n = search_strand_dev(a.v, a.p, fw[r], u.rdlen[r], st, L, a.full_cap);
 					if(n > a.full_cap) atomicExch(a.overflow, 1u);
 					u.L[r][st] = L; u.n[r][st] = min(n, a.full_cap);
 					a.regen_n[slot] = u.n[r][st]; a.nhits[tpos[r] + st] = kListRegen | (uint32_t)slot;
@@ -1771,6 +1834,7 @@ struct cfb_ctx {
 	TextCtx* text = nullptr;
 	CountsCtx cnt; bool fold_records = false;
 	uint32_t jump_w = 4; bool keep_short = false;      // CFB_KEEP_SHORT=1: store every hit (A/B and tests)
+	uint64_t regen_lists = 0, regen_tasks = 0;   // lists regenerated / strand lists searched so far (CFB_REGEN_STATS=1 prints them when the context goes)
 	uint64_t regen_slots0 = 0;    // CFB_REGEN_SLOTS: initial capacity of the list-regeneration buffer (tests force the grow-and-re-run path with it)
 	void* comm = nullptr; int comm_rank = 0, comm_size = 1; cudaStream_t comm_st = nullptr;      // NCCL communicator (cf_multi.cuh)
 };
@@ -1794,6 +1858,9 @@ static void expand_taxids(const HostIndex& h, const uint64_t* ids, uint64_t n, s
 extern "C" void cfb_ctx_destroy(cfb_ctx* c) {
 	if(!c) return;
 	if(c->ix && c->ix->device >= 0) cudaSetDevice(c->ix->device);
+	if(getenv("CFB_REGEN_STATS") && c->regen_tasks)
+		fprintf(stderr, "[cfb] strand lists regenerated by k_prep: %llu of %llu (%.3f %%)\n", (unsigned long long)c->regen_lists,
+		        (unsigned long long)c->regen_tasks, 100.0 * (double)c->regen_lists / (double)c->regen_tasks);
 	text_release(c);
 	comm_release(c);
 	c->cnt.release();
@@ -2226,6 +2293,7 @@ static int finish_batch(cfb_ctx* c, Slot& s, bool time_it, bool to_host, cfb_res
 		break;
 	}
 	const uint64_t nrec = s.h_scal.p[4];
+	c->regen_lists += s.h_scal.p[6]; c->regen_tasks += (uint64_t)s.n_units * (uint64_t)s.bv.n_mates * 2;
 	if(s.folded) {        // the batch is final: add its counters to the context's totals (stream order keeps this ahead of any read)
 		const uint32_t n3 = 3 * c->cnt.n;
 		k_cnt_commit<<<(n3 + 255) / 256, 256, 0, s.st>>>(s.cnt.p, c->cnt.total.p, n3); c->launches++;

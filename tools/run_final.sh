@@ -1,6 +1,12 @@
 #!/bin/bash
 # final round-2 lines of all four single-GPU configs + the ncu evidence of the default one
+if [ "${CFB_FINAL_TESTS:-1}" = 1 ]; then
+    timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/r2_tests_final.log 2>&1 || { tail -30 gpurun_out/r2_tests_final.log; echo "GPU TESTS FAILED -- no benches run"; exit 1; }
+    tail -2 gpurun_out/r2_tests_final.log
+fi
+export CFB_REGEN_STATS=1
 bash tools/run_profiles.sh
+CFB_CLI_GBP=9 timeout 600 python tools/cli_bench.py > gpurun_out/r2_cli_bench.txt 2>&1; tail -12 gpurun_out/r2_cli_bench.txt | cut -c1-400
 timeout 900 python bench.py --steps 20 --warmup 3 --lens 75-300 > gpurun_out/r2_bench_mixed.json 2> gpurun_out/r2_bench_mixed.err
 timeout 1200 python bench.py --steps 20 --warmup 3 --paired --rdlen 150 --index-gbp 17 > gpurun_out/r2_bench_pe150_17g.json 2> gpurun_out/r2_bench_pe150_17g.err
 rm -rf /tmp/cfb200_bench/cid_g1700_* /tmp/cfb200_bench/cid_g900_*
@@ -12,3 +18,4 @@ try:
 except Exception as e: print("no json:", e)
 PY
 done
+grep -h "regenerated" gpurun_out/r2_bench_*.err | sort | uniq -c | head -20
