@@ -113,14 +113,14 @@ class Reads:
         """arrays of a cfb_batch_packed: 2-bit words (mate 1 of all units, then mate 2), N positions"""
         words, npos, wbase = [], [], 0
         W = (self.lmax + 31) // 32
-        sh = (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, None, :]
         for m in range(self.mates):
             L = self.lens[m].astype(np.int64)
             valid = np.arange(self.lmax)[None, :] < L[:, None]
             isn = (self.codes[m] > 3) & valid
-            pad = np.zeros((self.n, W * 32), dtype=np.uint64)
+            pad = np.zeros((self.n, W * 32), dtype=np.uint8)
             pad[:, :self.lmax] = np.where(isn | ~valid, 0, self.codes[m])
-            w = (pad.reshape(self.n, W, 32) << sh).sum(axis=2, dtype=np.uint64)
+            q = pad.reshape(self.n, W * 8, 4)                     # four bases per byte, base j of a word at bits 2j (little-endian words)
+            w = (q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)).view("<u8")
             wl = (L + 31) // 32
             keep = np.arange(W)[None, :] < wl[:, None]
             words.append(w[keep])
@@ -137,7 +137,7 @@ class Reads:
         fl = pin((self.n,), np.uint8); fl[:] = self.flags()
         return pw, pn, lens, fl
 
-    def fastq(self, m, start=0, suffix=b""):
+    def fastq(self, m, start=0, suffix=b"", force_general=False):
         """FASTQ text of mate m: "@r%09d<suffix>", bases, "+", qualities 'I' (vectorised, variable lengths)"""
         n = self.n
         L = self.lens[m].astype(np.int64)
@@ -147,11 +147,21 @@ class Reads:
         out = np.full(int(rec.sum()), ord("I"), dtype=np.uint8)
         hdr = np.empty((n, hl + 1), dtype=np.uint8)
         hdr[:, 0] = ord("@"); hdr[:, 1] = ord("r")
-        idx = np.arange(start, start + n, dtype=np.int64)
-        hdr[:, 2:11] = (idx[:, None] // (10 ** np.arange(8, -1, -1, dtype=np.int64))[None, :] % 10 + 48).astype(np.uint8)
+        v = np.arange(start, start + n, dtype=np.int64).astype(np.uint32)
+        for k in range(8, -1, -1):                              # nine decimal digits, last first
+            q = v // 10
+            hdr[:, 2 + k] = (v - q * 10 + 48).astype(np.uint8); v = q
         if suffix:
             hdr[:, 11:11 + len(suffix)] = np.frombuffer(suffix, dtype=np.uint8)[None, :]
         hdr[:, hl] = 10
+        if n and not force_general and int(L.min()) == int(L.max()):          # one length: the records are the rows of a 2-D array
+            l = int(L[0])
+            rows = out.reshape(n, int(rec[0]))
+            rows[:, :hl + 1] = hdr
+            rows[:, hl + 1:hl + 1 + l] = np.frombuffer(b"ACGTN", dtype=np.uint8)[self.codes[m][:, :l]]
+            rows[:, hl + 1 + l:hl + 4 + l] = np.array([10, 43, 10], dtype=np.uint8)[None, :]
+            rows[:, -1] = 10
+            return out
         out[(off[:, None] + np.arange(hl + 1)[None, :]).reshape(-1)] = hdr.reshape(-1)
         mask = np.arange(self.lmax)[None, :] < L[:, None]
         pos = (off + hl + 1)[:, None] + np.arange(self.lmax)[None, :]
